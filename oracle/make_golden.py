@@ -1,0 +1,156 @@
+"""Generate tests/golden/*.npz by executing the REAL reference (build container only).
+
+TEST INFRASTRUCTURE.  Run as `python -m oracle.make_golden` from the repo root in the build
+container, where /root/reference exists.  The reference's `src/utils/idealscore.py` is imported
+unmodified (behind a matplotlib stub, oracle/ref_loader.py) and its LS / ELS / bbELS modules and
+`ScheduledScoreMachine` are executed on CPU (true fp32) on small seeded banks.  Inputs AND outputs
+are stored, so the fixtures are self-contained: the GPU box has no /root/reference.
+
+Every case is a dict of arrays:
+    kind, bank [N,C,H,W] f32, labels [N] i64, x [1,C,H,W] f32, t, k, label (-1 = None),
+    batch_size, max_samples (-1 = None), score [1,C,H,W] f32   (module cases)
+    kind, bank, labels, x, scales, label, batch_size, out [1,C,H,W]   (machine cases)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from convolutional_diffusion_b200.synthetic import synthetic_bank  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _module(ref, kind, ds, k, bs, max_samples):
+    if kind == "ELS":
+        return ref.LocalEquivScoreModule(ds, kernel_size=k, batch_size=bs, max_samples=max_samples,
+                                         schedule=ref.cosine_noise_schedule)
+    if kind == "bbELS":
+        return ref.LocalEquivBordersScoreModule(ds, kernel_size=k, batch_size=bs, max_samples=max_samples,
+                                                schedule=ref.cosine_noise_schedule)
+    if kind == "LS":
+        return ref.LocalScoreModule(ds, kernel_size=k, batch_size=bs, max_samples=max_samples,
+                                    schedule=ref.cosine_noise_schedule)
+    raise ValueError(kind)
+
+
+def module_cases(ref):
+    cases = []
+    # (kind, C, H, N, k, t, label, batch_size, max_samples, bank_seed)
+    spec = [
+        ("ELS", 3, 12, 40, 3, 0.30, None, 16, None, 0),     # short last batch -> mean quirk
+        ("ELS", 3, 12, 40, 5, 0.55, 3, 16, None, 0),        # label filter -> unequal n_b
+        ("ELS", 1, 12, 48, 7, 0.80, None, 16, None, 1),
+        ("ELS", 1, 16, 32, 3, 0.05, None, 32, None, 2),     # low noise, sharp softmax
+        ("ELS", 3, 16, 48, 9, 0.95, 1, 12, 30, 3),          # max_samples break (pre-filter count)
+        ("ELS", 3, 8, 24, 5, 0.50, None, 8, None, 4),
+        ("bbELS", 3, 12, 40, 3, 0.30, None, 16, None, 0),
+        ("bbELS", 3, 12, 40, 5, 0.55, 3, 16, None, 0),
+        ("bbELS", 1, 12, 48, 7, 0.80, None, 16, None, 1),
+        ("bbELS", 1, 16, 32, 3, 0.05, None, 32, None, 2),
+        ("bbELS", 3, 16, 48, 9, 0.95, 1, 12, 30, 3),        # q += batch_size bookkeeping
+        ("bbELS", 3, 32, 8, 17, 0.90, None, 8, None, 5),    # CIFAR shape, k=17 (cfg-4 geometry)
+        ("LS", 3, 12, 40, 3, 0.30, None, 40, None, 0),      # drivers use one giant batch
+        ("LS", 1, 12, 48, 5, 0.55, None, 48, None, 1),
+        ("LS", 3, 16, 48, 7, 0.80, 2, 48, None, 3),
+        ("LS", 1, 28, 24, 5, 0.40, None, 24, None, 6),      # MNIST native shape (cfg-1 geometry)
+        ("LS", 3, 12, 40, 3, 0.30, None, 8, None, 0),       # equal batches: order independent
+    ]
+    for kind, c, h, n, k, t, label, bs, ms, seed in spec:
+        bank, labels = synthetic_bank(n, c, h, nlabels=4, seed=seed)
+        g = torch.Generator().manual_seed(100 + seed)
+        j = int(torch.randint(0, n, (1,), generator=g))
+        tt = torch.tensor([t])
+        beta = float(ref.cosine_noise_schedule(tt))
+        x = (1 - beta) ** 0.5 * bank[j:j + 1] + beta ** 0.5 * torch.randn(1, c, h, h, generator=g)
+        ds = ref_loader.TensorBank(bank, labels)
+        torch.manual_seed(0)
+        mod = _module(ref, kind, ds, k, bs, ms)
+        lab = None if label is None else torch.tensor([label])
+        with torch.no_grad():
+            s = mod(tt, x.clone(), label=lab, device=torch.device("cpu"))
+        cases.append(dict(kind=kind, bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(), t=np.float64(t),
+                          k=np.int64(k), label=np.int64(-1 if label is None else label),
+                          batch_size=np.int64(bs), max_samples=np.int64(-1 if ms is None else ms),
+                          score=s.numpy()))
+        print(f"module {kind:5s} C={c} H={h} N={n} k={k} t={t} label={label}: |score|max={s.abs().max():.3f}")
+    # bbELS with k >= H delegates to its internal LS (idealscore.py:163-164); single batch so the
+    # hard-coded shuffle=True cannot change the result
+    bank, labels = synthetic_bank(16, 3, 8, nlabels=4, seed=7)
+    g = torch.Generator().manual_seed(107)
+    x = torch.randn(1, 3, 8, 8, generator=g)
+    tt = torch.tensor([0.6])
+    mod = _module(ref, "bbELS", ref_loader.TensorBank(bank, labels), 9, 16, None)
+    with torch.no_grad():
+        s = mod(tt, x.clone(), device=torch.device("cpu"), k=9)
+    cases.append(dict(kind="bbELS", bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(), t=np.float64(0.6),
+                      k=np.int64(9), label=np.int64(-1), batch_size=np.int64(16), max_samples=np.int64(-1),
+                      score=s.numpy()))
+    return cases
+
+
+def machine_cases(ref):
+    cases = []
+    spec = [
+        ("ELS", 3, 12, 32, [3, 3, 3, 5, 5, 7], None, 16, 10),
+        ("ELS", 1, 12, 36, [3, 3, 5, 5, 7, 7, 9, 9], 2, 12, 11),
+        ("bbELS", 3, 12, 32, [3, 3, 3, 5, 5, 7], None, 16, 10),
+        ("bbELS", 1, 12, 36, [3, 3, 5, 5, 7, 7, 9, 13], 2, 12, 11),   # last k >= H -> LS fallback, 1 batch/class
+        ("LS", 3, 12, 32, [3, 3, 3, 5, 5, 7], None, 32, 10),
+    ]
+    for kind, c, h, n, scales, label, bs, seed in spec:
+        bank, labels = synthetic_bank(n, c, h, nlabels=3, seed=seed)
+        ds = ref_loader.TensorBank(bank, labels)
+        if kind == "bbELS" and max(scales) >= h:
+            bs = n  # keep the internal shuffled LS single-batch so the golden is order independent
+        torch.manual_seed(0)
+        mod = _module(ref, kind, ds, 3, bs, None)
+        machine = ref.ScheduledScoreMachine(mod, in_channels=c, imsize=h, scales=scales, score_backbone=True)
+        g = torch.Generator().manual_seed(200 + seed)
+        x = torch.randn(1, c, h, h, generator=g)
+        lab = None if label is None else torch.tensor([label])
+        with torch.no_grad():
+            out = machine(x.clone(), label=lab, device=torch.device("cpu"))
+        cases.append(dict(kind=kind, bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(),
+                          scales=np.asarray(scales, dtype=np.int64), label=np.int64(-1 if label is None else label),
+                          batch_size=np.int64(bs), out=out.numpy()))
+        print(f"machine {kind:5s} C={c} H={h} N={n} scales={scales} label={label}: |out|max={out.abs().max():.3f}")
+    return cases
+
+
+def schedule_cases(ref):
+    t = torch.arange(0, 21, dtype=torch.float32) / 20
+    return dict(t=t.numpy(), cosine=ref.cosine_noise_schedule(t).numpy(),
+                exponential=ref.exponential_schedule(t).numpy())
+
+
+def scales_files():
+    import glob
+    out = {}
+    for f in sorted(glob.glob(os.path.join(ref_loader.REF_DIR, "checkpoints", "scales_*.pt"))):
+        out[os.path.basename(f)[:-3]] = np.asarray(torch.load(f, weights_only=False), dtype=np.int64)
+    return out
+
+
+def main():
+    ref = ref_loader.load()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for i, c in enumerate(module_cases(ref)):
+        np.savez_compressed(os.path.join(OUT, f"module_{i:02d}_{c['kind']}.npz"), **c)
+    for i, c in enumerate(machine_cases(ref)):
+        np.savez_compressed(os.path.join(OUT, f"machine_{i:02d}_{c['kind']}.npz"), **c)
+    np.savez_compressed(os.path.join(OUT, "schedule.npz"), **schedule_cases(ref))
+    np.savez_compressed(os.path.join(OUT, "scales.npz"), **scales_files())
+
+
+if __name__ == "__main__":
+    main()
