@@ -1,0 +1,71 @@
+"""ctypes binding of the C ABI in include/cdscore.h (libcdscore.so, built in-tree by build.py).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcdscore.so")
+
+KIND = {"LS": 0, "ELS": 1, "bbELS": 2}
+PAD = {"zeros": 0, "circular": 1}
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+
+# name -> (restype, argtypes); mirrors include/cdscore.h one to one
+SIGNATURES = {
+    "cds_abi_version": (_i, []),
+    "cds_last_error": (C.c_char_p, []),
+    "cds_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "cds_pack_strip8": (_i, [_p, _i64, _i, _i, _i, _f, _i, _p, _p]),
+    "cds_patch_norms": (_i, [_p, _i64, _i, _i, _i, _i, _p, _p]),
+    "cds_partials_simt": (_i, [_i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
+    "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,
+                                   _p, _p, _p, _p, _p]),
+    "cds_els_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "cds_combine": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "cds_finalize": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "cds_ddim_step": (_i, [_p, _p, _p, _p, _i, _i64, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library; raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -m convolutional_diffusion_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cds_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,114 @@
+"""The training-patch bank, resident in HBM.
+
+The reference re-reads and re-transforms the whole dataset through a DataLoader on every score evaluation
+(`/root/reference/src/utils/idealscore.py:184,430,521`) and copies each batch host->device inside the hot loop
+(:441).  Here the images are uploaded once and kept in two layouts:
+
+  images  fp32 planar [N,C,H,W]            exact values; SIMT kernels, patch norms, LS stream
+  strip8  bf16 [N,C,H,W,8] (+ residual)    tensor-core stream: one 16-byte granule = 8 vertically adjacent
+                                           pixels, so overlapping k x k patches alias the same bytes
+                                           (implicit im2col, see csrc/els_umma.cu)
+
+8-bit image datasets normalised with mean 0.5 / std 0.5 (`src/utils/data.py:63-70`) are odd integers / 255,
+which bf16 represents exactly after scaling by 255 -> a single bf16 plane carries the bank losslessly.
+Other banks get a second residual plane.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .selection import select, shard
+
+
+def dataset_to_tensors(dataset):
+    """Materialises a map-style dataset of (image [C,H,W], label) pairs (the protocol of
+    idealscore.py:142,390,489) into (images [N,C,H,W] float32, labels [N] int64) on the host."""
+    if isinstance(dataset, (tuple, list)) and len(dataset) == 2 and torch.is_tensor(dataset[0]):
+        return dataset[0].float().contiguous(), torch.as_tensor(dataset[1]).long()
+    imgs = getattr(dataset, "images", None)
+    labs = getattr(dataset, "labels", None)
+    if torch.is_tensor(imgs) and labs is not None and imgs.dim() == 4:
+        return imgs.float().contiguous(), torch.as_tensor(labs).long()
+    if isinstance(dataset, torch.utils.data.Subset):
+        base_i, base_l = dataset_to_tensors(dataset.dataset)
+        sel = torch.as_tensor(list(dataset.indices), dtype=torch.long)
+        return base_i[sel].contiguous(), base_l[sel]
+    if isinstance(dataset, torch.utils.data.TensorDataset) and len(dataset.tensors) == 2:
+        return dataset.tensors[0].float().contiguous(), dataset.tensors[1].long()
+    n = len(dataset)
+    first, _ = dataset[0]
+    images = torch.empty((n,) + tuple(first.shape), dtype=torch.float32)
+    labels = torch.empty(n, dtype=torch.long)
+    for i in range(n):
+        im, lab = dataset[i]
+        images[i] = im
+        labels[i] = int(lab)
+    return images, labels
+
+
+class PatchBank:
+    def __init__(self, images, labels, device=None):
+        self.lib = _lib.load()                                   # raises if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("PatchBank needs a CUDA device: the score machines have no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError(f"PatchBank device must be CUDA, got {self.device}")
+        assert images.dim() == 4, "bank images must be [N,C,H,W]"
+        self.images = images.to(self.device, torch.float32).contiguous()
+        self.labels = np.asarray(torch.as_tensor(labels).cpu()).astype(np.int64).reshape(-1)
+        self.N, self.C, self.H, self.W = self.images.shape
+        assert self.labels.shape[0] == self.N
+        self._strip = None
+        self._pnorm = {}
+        self._sel = {}
+
+    # ---- layouts -------------------------------------------------------------------------------
+    def strip8(self):
+        """(hi, lo or None, scale): the bf16 strip layout for the tensor-core kernel."""
+        if self._strip is None:
+            with torch.cuda.device(self.device):
+                v = self.images * 127.5 + 127.5                    # back to the 0..255 grid of ToTensor()
+                exact8 = bool(((v - v.round()).abs().max() < 1e-3).item()) and bool((v.min() > -0.5).item()) \
+                    and bool((v.max() < 255.5).item())
+                scale = 255.0 if exact8 else 1.0
+                n = self.N * self.C * self.H * self.W
+                hi = torch.empty(n * 8, dtype=torch.bfloat16, device=self.device)
+                _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
+                                                    scale, 0, _lib.ptr(hi), _lib.stream_ptr()), "cds_pack_strip8")
+                lo = None
+                if not exact8:
+                    lo = torch.empty(n * 8, dtype=torch.bfloat16, device=self.device)
+                    _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
+                                                        scale, 1, _lib.ptr(lo), _lib.stream_ptr()), "cds_pack_strip8")
+                self._strip = (hi, lo, scale)
+        return self._strip
+
+    def patch_norms(self, k):
+        """||p||^2 of every valid k x k x C patch, [N, (H-k+1)*(W-k+1)] fp32 (computed once per k)."""
+        if k not in self._pnorm:
+            with torch.cuda.device(self.device):
+                out = torch.empty(self.N * (self.H - k + 1) * (self.W - k + 1), dtype=torch.float32, device=self.device)
+                _lib.check(self.lib.cds_patch_norms(_lib.ptr(self.images), self.N, self.C, self.H, self.W, k,
+                                                    _lib.ptr(out), _lib.stream_ptr()), "cds_patch_norms")
+                self._pnorm[k] = out
+        return self._pnorm[k]
+
+    # ---- selection -----------------------------------------------------------------------------
+    def selection(self, kind, label, batch_size, max_samples, order=None, rank=0, world=1):
+        """(idx int32 device, logw fp32 device, n_sel) for one score evaluation; cached per key when the
+        visiting order is the identity."""
+        key = (kind, label, batch_size, max_samples, rank, world) if order is None else None
+        if key is not None and key in self._sel:
+            return self._sel[key]
+        idx, logw = select(kind, self.labels, label, batch_size, max_samples, order)
+        if idx.shape[0] == 0:
+            raise RuntimeError(f"no bank image selected (kind={kind}, label={label}, max_samples={max_samples})")
+        idx, logw = shard(idx, logw, rank, world)
+        out = (torch.from_numpy(idx.astype(np.int32)).to(self.device),
+               torch.from_numpy(logw.astype(np.float32)).to(self.device), int(idx.shape[0]))
+        if key is not None:
+            self._sel[key] = out
+        return out

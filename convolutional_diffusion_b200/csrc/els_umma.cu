@@ -1,0 +1,533 @@
+// ELS score partials on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators) with implicit im2col.
+//
+// What it computes (reference: /root/reference/src/utils/idealscore.py:397-473, restated):
+//   for every query pixel (i,j) of x (k x k x C patch of the padded image) and every valid k x k x C patch
+//   p(n,u,v) of every selected bank image:  logit = -(|q|^2 - 2a q.p + a^2 |p|^2)/(2 beta) + logw_n,
+//   online softmax over all (n,u,v), weighted sum of the patch-centre pixels.  |q|^2 is constant per query
+//   and cancels in the softmax, so it is dropped from the logits (the partial max m is in those units).
+//
+// How (B200-first, not a translation of unfold+conv2d):
+//   * The bank lives in HBM as "strip8": one 16-byte granule = 8 vertically adjacent pixels
+//     [n][c][u][x][8] bf16.  With K-major, no-swizzle UMMA descriptors the row pitch inside an 8-row core
+//     matrix is 16 bytes, so 8 consecutive B rows = 8 horizontally adjacent patches, the next K granule
+//     (LBO = 16 B) = the next patch column dx, and the 8-row-group stride (SBO = one image row of granules)
+//     = the next patch row u.  Overlapping patches therefore alias the SAME shared-memory bytes: patches are
+//     never materialised, in HBM or in shared memory.  A whole image is staged by one cp.async.bulk.
+//   * The query side uses the same trick on a per-CTA tile of 16 x 8 pixels, with the K padding (dy >= k)
+//     zeroed on the query side only, so the bank can stay unmasked and k-independent.
+//   * One UMMA covers N = 8 * (#patch rows) <= 256 candidates x 128 queries x K = 16; accumulators ping-pong
+//     between two TMEM buffers; a producer warp, an MMA warp and two epilogue warpgroups run decoupled
+//     through mbarriers.  The epilogue is the flash-softmax: tcgen05.ld -> fma -> max -> ex2 -> weighted sum.
+#include "common.cuh"
+#include "../../include/cdscore.h"
+
+namespace {
+
+constexpr int TI = 16, TJ = 8;           // query tile: 16 rows x 8 columns = 128 queries = UMMA M
+constexpr int NUM_STAGES = 2;
+constexpr int MAX_CHUNKS = 4;
+constexpr int THREADS = 128 + 256;       // 4 control warps + 2 epilogue warpgroups
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_MMAS = 192;
+
+struct UmmaGeom {
+  int C, H, W, k, d, Ph, Pw, Ppad;
+  int nb;             // dy blocks of 8 rows
+  int RA;             // bytes between query rows in the A tile = (k+7)*16
+  int a_block;        // bytes of one (c,b) block of A = TI*RA
+  int a_plane;        // bytes of one precision plane of A = C*nb*a_block
+  int a_zero;         // byte offset of the zero block in A
+  int a_bytes;        // total A bytes (planes + zero block)
+  int S1;             // bytes of one image row of granules = W*16
+  int img_bytes;      // C*H*W*16
+  int tile_pad;       // zeroed guard after each B tile
+  int stage_bytes;    // bank_planes*(img_bytes+tile_pad) + Ppad*4, rounded to 128
+  int pn_off;         // offset of the norms inside a stage
+  int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
+  int nvb;            // 8-column blocks of candidate patches
+  int n_mma;          // table entries (per precision combination)
+  int passes, bank_planes;
+  int smem_A, smem_stage, smem_colinfo, smem_table, smem_bar, smem_total;
+};
+
+struct UmmaParams {
+  UmmaGeom g;
+  int B, pad, splits;
+  long long n_sel;
+  const float* x;
+  const float* beta;
+  const uint8_t* bank_hi;
+  const uint8_t* bank_lo;
+  float inv_scale;
+  const float* pnorm;
+  const int32_t* idx;
+  const float* logw;
+  float *m, *l, *acc, *dbg;
+  uint2 table[MAX_MMAS];   // lo words of (A,B) descriptors relative to their bases
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must become a trap (CUDA error), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  for (uint32_t it = 0; it < (1u << 22); ++it)
+    if (mbar_try(bar, parity)) return;
+  printf("cdscore: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major, no-swizzle shared memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4   [16,30) LBO>>4 (stride between the two K granules)   [32,46) SBO>>4 (stride between
+//   8-row groups)   [46,48) version = 1   [61,64) layout = 0 (interleave / no swizzle)
+__device__ __forceinline__ uint64_t desc_hi(uint32_t sbo_bytes) {
+  return ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int C>
+__global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_constant__ UmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const UmmaGeom& g = p.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_j = (g.W + TJ - 1) / TJ;
+  const int i0 = (blockIdx.x / tiles_j) * TI, j0 = (blockIdx.x % tiles_j) * TJ;
+  const int split = blockIdx.y, b = blockIdx.z;
+  const long long n0 = p.n_sel * split / p.splits, n1 = p.n_sel * (split + 1) / p.splits;
+  const int n_img = (int)(n1 - n0);
+  const int tiles_per_img = g.nchunks * g.nvb;
+
+  uint8_t* sA = smem;
+  uint8_t* sStage = smem + g.smem_A;
+  float4* sCol = reinterpret_cast<float4*>(smem + g.smem_A + g.smem_stage);          // [2][256]
+  uint2* sTable = reinterpret_cast<uint2*>(smem + g.smem_A + g.smem_stage + g.smem_colinfo);
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + g.smem_A + g.smem_stage + g.smem_colinfo + g.smem_table);
+  // barriers: full[S], empty[S], tfull[2], tempty[2]; then tmem base; then the WG1 -> WG0 merge scratch
+  const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 8 * NUM_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * NUM_STAGES, bar_tempty = bar_tfull + 16;
+  uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sBar + 2 * NUM_STAGES + 4);
+  float* sMerge = reinterpret_cast<float*>(sBar + 2 * NUM_STAGES + 6);               // [128][2+C]
+
+  const float beta = p.beta[b];
+  const float a = sqrtf(1.f - beta);
+
+  // ---- one-time setup: barriers, TMEM, descriptor table, zero guards, query tile (A operand)
+  if (tid == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1 + 8);   // MMA commit + 8 epilogue warps
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(bar_tfull + 8 * q, 1);
+      mbar_init(bar_tempty + 8 * q, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
+  for (int e = tid; e < g.n_mma; e += THREADS) sTable[e] = p.table[e];
+  // zero guards behind every staged image tile (over-reads of masked columns must stay finite)
+  for (int s = 0; s < NUM_STAGES; ++s)
+    for (int pl = 0; pl < g.bank_planes; ++pl) {
+      uint8_t* pad = sStage + (size_t)s * g.stage_bytes + (size_t)pl * (g.img_bytes + g.tile_pad) + g.img_bytes;
+      for (int e = tid * 16; e < g.tile_pad; e += THREADS * 16) *reinterpret_cast<uint4*>(pad + e) = make_uint4(0, 0, 0, 0);
+    }
+  {
+    // A[plane][c][blk][gi][jj][8]: element e of granule (gi,jj) of block blk = xpad[i0+gi+8*blk+e][j0+jj] (patch
+    // coordinates: padded row = pixel row + dy, i.e. source pixel row i0+gi+dy-d), zero where dy = 8*blk+e >= k
+    const int JW = g.k + 7;
+    const int per_plane = C * g.nb * TI * JW;
+    const float* xb = p.x + (size_t)b * C * g.H * g.W;
+    for (int e = tid; e < per_plane; e += THREADS) {
+      const int jj = e % JW, gi = (e / JW) % TI, blk = (e / (JW * TI)) % g.nb, c = e / (JW * TI * g.nb);
+      __nv_bfloat16 hi[8], lo[8];
+      int xc = j0 + jj - g.d;
+      bool colok = true;
+      if (p.pad == CDS_PAD_CIRCULAR) xc = ((xc % g.W) + g.W) % g.W;
+      else colok = (xc >= 0 && xc < g.W);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int dy = 8 * blk + q;
+        int yr = i0 + gi + dy - g.d;
+        bool ok = colok && dy < g.k;
+        if (p.pad == CDS_PAD_CIRCULAR) yr = ((yr % g.H) + g.H) % g.H;
+        else ok = ok && (yr >= 0 && yr < g.H);
+        const float v = ok ? xb[(c * g.H + yr) * g.W + xc] : 0.f;
+        hi[q] = __float2bfloat16_rn(v);
+        lo[q] = __float2bfloat16_rn(v - __bfloat162float(hi[q]));
+      }
+      const size_t off = (size_t)(c * g.nb + blk) * g.a_block + (size_t)gi * g.RA + (size_t)jj * 16;
+      *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<uint4*>(hi);
+      if (g.passes > 1) *reinterpret_cast<uint4*>(sA + g.a_plane + off) = *reinterpret_cast<uint4*>(lo);
+    }
+    for (int e = tid * 16; e < g.a_block; e += THREADS * 16)
+      *reinterpret_cast<uint4*>(sA + g.a_zero + e) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sTmemBase;
+
+  if (warp == 0) {
+    // =========================== producer: one bulk copy per image (+ its patch norms)
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(g.bank_planes * g.img_bytes + g.Ppad * 4);
+      for (int n = 0; n < n_img; ++n) {
+        const int s = n % NUM_STAGES;
+        const uint32_t ph = (n / NUM_STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
+        const long long gi = p.idx[n0 + n];
+        const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
+        mbar_expect_tx(bar_full + 8 * s, tx);
+        bulk_g2s(dst, p.bank_hi + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
+        if (g.bank_planes > 1)
+          bulk_g2s(dst + g.img_bytes + g.tile_pad, p.bank_lo + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
+        bulk_g2s(dst + g.pn_off, p.pnorm + (size_t)gi * g.Ppad, g.Ppad * 4, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (single thread)
+    if (lane == 0) {
+      const uint64_t a_hi = desc_hi(g.RA), b_hi = desc_hi(g.S1);
+      const uint32_t a_base = smem_u32(sA) >> 4;
+      long long T = 0;
+      for (int n = 0; n < n_img; ++n) {
+        const int s = n % NUM_STAGES;
+        mbar_wait(bar_full + 8 * s, (n / NUM_STAGES) & 1, 2);
+        tc_fence_after();
+        const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
+        for (int ch = 0; ch < g.nchunks; ++ch) {
+          const uint32_t N = 8u * g.chunk_g[ch];
+          // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+          // N>>3 at [17,23), M>>4 at [24,29)
+          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+          for (int vb = 0; vb < g.nvb; ++vb, ++T) {
+            const int buf = (int)(T & 1);
+            mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((T >> 1) & 1) ^ 1), 3);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * 256;
+            uint32_t accum = 0;
+            // precision combinations: (query plane, bank plane) = (0,0) [,(1,0)] [,(0,1)]
+            const int ncomb = g.passes + g.bank_planes - 1;
+            for (int cb = 0; cb < ncomb; ++cb) {
+              const int pa = (cb == 1 && g.passes > 1) ? 1 : 0;
+              const int pb = (cb == ncomb - 1 && g.bank_planes > 1 && cb > 0) ? 1 : 0;
+              const uint32_t a_off = a_base + ((uint32_t)(pa * g.a_plane) >> 4);
+              const uint32_t b_off =
+                  (stage_addr + (uint32_t)pb * (g.img_bytes + g.tile_pad) + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
+              for (int t = 0; t < g.n_mma; ++t) {
+                const uint2 e = sTable[t];
+                umma_bf16(d_tmem, a_hi | (uint64_t)(e.x + a_off), b_hi | (uint64_t)(e.y + b_off), idesc, accum);
+                accum = 1;
+              }
+            }
+            umma_commit(bar_tfull + 8 * buf);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue: two warpgroups, tile T handled by warpgroup T&1 from TMEM buffer T&1
+    const int wg = (warp - 4) >> 2, q = tid - 128 - wg * 128;   // q = query row = TMEM lane
+    const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
+    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+    float4* col = sCol + wg * 256;
+    const float c1 = CDS_LOG2E * a / beta * p.inv_scale;
+    const float cpn = -CDS_LOG2E * a * a / (2.f * beta);
+    float m = -INFINITY, l = 0.f, acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float* dbg = (p.dbg && split == 0 && qi < g.H && qj < g.W)
+                     ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
+                     : nullptr;
+    long long T = 0;
+    for (int n = 0; n < n_img; ++n) {
+      const int s = n % NUM_STAGES;
+      mbar_wait(bar_full + 8 * s, (n / NUM_STAGES) & 1, 4);
+      const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
+      const float* pn = reinterpret_cast<const float*>(st + g.pn_off);
+      const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
+      for (int ch = 0; ch < g.nchunks; ++ch) {
+        const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
+        for (int vb = 0; vb < g.nvb; ++vb, ++T) {
+          if ((int)(T & 1) != wg) continue;
+          const int buf = wg;
+          // per-column bias and centre pixel of this tile's candidates: column r = 8*gr + rr <-> (u0+gr, 8*vb+rr)
+          bar_sync_named(1 + wg, 128);   // everyone done reading col[] of the previous tile
+          for (int r = q; r < N; r += 128) {
+            const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
+            const bool valid = (u < g.Ph) && (v < g.Pw);
+            float4 ci;
+            ci.x = valid ? fmaf(pn[valid ? u * g.Pw + v : 0], cpn, lw) : -INFINITY;
+            float vals[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const size_t go = ((size_t)(c * g.H + u + g.d) * g.W + (v + g.d)) * 16;
+              float t = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(st + go));
+              if (g.bank_planes > 1)
+                t += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(st + g.img_bytes + g.tile_pad + go));
+              vals[c] = valid ? t * p.inv_scale : 0.f;
+            }
+            ci.y = vals[0]; ci.z = vals[1]; ci.w = vals[2];
+            col[r] = ci;
+          }
+          bar_sync_named(1 + wg, 128);
+          mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
+          for (int c0 = 0; c0 < N; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            float t[16], cmax = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              t[e] = fmaf(__uint_as_float(r[e]), c1, col[c0 + e].x);
+              cmax = fmaxf(cmax, t[e]);
+            }
+            if (dbg && n == 0) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int u = u0 + ((c0 + e) >> 3), v = 8 * vb + ((c0 + e) & 7);
+                if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[e]) * p.inv_scale;
+              }
+            }
+            const float m_new = fmaxf(m, cmax);
+            const float sc = ex2(m - m_new);
+            l *= sc;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] *= sc;
+            m = m_new;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float4 ci = col[c0 + e];
+              const float w = ex2(t[e] - m);
+              l += w;
+              acc[0] = fmaf(w, ci.y, acc[0]);
+              if (C > 1) acc[1 % C] = fmaf(w, ci.z, acc[1 % C]);
+              if (C > 2) acc[2 % C] = fmaf(w, ci.w, acc[2 % C]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
+    // merge the two warpgroups' partial softmax states and write this split's partials
+    if (wg == 1) {
+      sMerge[q * (2 + C) + 0] = m;
+      sMerge[q * (2 + C) + 1] = l;
+#pragma unroll
+      for (int c = 0; c < C; ++c) sMerge[q * (2 + C) + 2 + c] = acc[c];
+    }
+    bar_sync_named(3, 256);
+    if (wg == 0 && qi < g.H && qj < g.W) {
+      const float m1 = sMerge[q * (2 + C) + 0], l1 = sMerge[q * (2 + C) + 1];
+      const float M = fmaxf(m, m1);
+      const float w0 = (m == -INFINITY) ? 0.f : ex2(m - M), w1 = (m1 == -INFINITY) ? 0.f : ex2(m1 - M);
+      const int HW = g.H * g.W, pix = qi * g.W + qj;
+      const size_t o = ((size_t)split * p.B + b) * HW + pix;
+      p.m[o] = M;
+      p.l[o] = l * w0 + l1 * w1;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        p.acc[(((size_t)split * p.B + b) * C + c) * HW + pix] = acc[c] * w0 + sMerge[q * (2 + C) + 2 + c] * w1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side: geometry + descriptor table
+int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom& g, uint2* table) {
+  if (C < 1 || C > 3 || H > 32 || W > 32 || H < k || W < k || (k & 1) == 0 || k < 3) return 0;
+  if (passes < 1 || passes > 2 || bank_planes < 1 || bank_planes > 2) return 0;
+  g.C = C; g.H = H; g.W = W; g.k = k; g.d = k / 2;
+  g.Ph = H - k + 1; g.Pw = W - k + 1;
+  g.Ppad = g.Ph * g.Pw;
+  if (g.Ppad % 4) return 0;   // norms are bulk-copied: 16-byte multiples only
+  g.nb = (k + 7) / 8;
+  g.RA = (k + 7) * 16;
+  g.a_block = TI * g.RA;
+  g.a_plane = C * g.nb * g.a_block;
+  g.a_zero = passes * g.a_plane;
+  g.a_bytes = g.a_zero + g.a_block;
+  g.S1 = W * 16;
+  g.img_bytes = C * H * W * 16;
+  g.tile_pad = ((k + 8) * 16 + 127) / 128 * 128;
+  g.pn_off = bank_planes * (g.img_bytes + g.tile_pad);
+  g.stage_bytes = (g.pn_off + g.Ppad * 4 + 127) / 128 * 128;
+  g.passes = passes; g.bank_planes = bank_planes;
+  // patch-row chunks: N = 8*G <= 256, G even (UMMA M=128 needs N % 16 == 0)
+  int rows = g.Ph, u0 = 0;
+  g.nchunks = 0;
+  while (rows > 0) {
+    if (g.nchunks == MAX_CHUNKS) return 0;
+    int G = rows > 32 ? 32 : rows;
+    int Ge = (G + 1) & ~1;
+    if (Ge < 2) Ge = 2;
+    g.chunk_u0[g.nchunks] = u0; g.chunk_g[g.nchunks] = Ge;
+    ++g.nchunks; u0 += G; rows -= G;
+  }
+  g.nvb = (g.Pw + 7) / 8;
+  // a rounded-up last patch row must stay inside the strip array: u + 8*(nb-1) <= H-1
+  if (g.chunk_u0[g.nchunks - 1] + g.chunk_g[g.nchunks - 1] - 1 + 8 * (g.nb - 1) > H - 1) return 0;
+  // K granule list (c, blk, dx); pairs (dx,dx+1) inside a block, leftovers paired across blocks, last with zeros
+  struct Gran { int a, b; };
+  int nm = 0;
+  Gran left[64]; int nleft = 0;
+  for (int c = 0; c < C; ++c)
+    for (int blk = 0; blk < g.nb; ++blk) {
+      const int a0 = (c * g.nb + blk) * g.a_block, b0 = (c * H + 8 * blk) * g.S1;
+      int dx = 0;
+      for (; dx + 1 < k; dx += 2) {
+        if (nm >= MAX_MMAS) return 0;
+        table[nm].x = (uint32_t)((a0 + dx * 16) >> 4) | (1u << 16);   // LBO = 16 B
+        table[nm].y = (uint32_t)((b0 + dx * 16) >> 4) | (1u << 16);
+        ++nm;
+      }
+      if (dx < k) { left[nleft].a = a0 + dx * 16; left[nleft].b = b0 + dx * 16; ++nleft; }
+    }
+  for (int q = 0; q < nleft; q += 2) {
+    if (nm >= MAX_MMAS) return 0;
+    if (q + 1 < nleft) {
+      table[nm].x = (uint32_t)(left[q].a >> 4) | ((uint32_t)((left[q + 1].a - left[q].a) >> 4) << 16);
+      table[nm].y = (uint32_t)(left[q].b >> 4) | ((uint32_t)((left[q + 1].b - left[q].b) >> 4) << 16);
+    } else {
+      // second K granule: zeros on the query side (A), any finite bank data on the B side
+      table[nm].x = (uint32_t)(left[q].a >> 4) | ((uint32_t)((g.a_zero - left[q].a) >> 4) << 16);
+      table[nm].y = (uint32_t)(left[q].b >> 4) | (1u << 16);
+    }
+    ++nm;
+  }
+  g.n_mma = nm;
+  g.smem_A = (g.a_bytes + 1023) / 1024 * 1024;
+  g.smem_stage = NUM_STAGES * g.stage_bytes;
+  g.smem_colinfo = 2 * 256 * 16;
+  g.smem_table = (nm * 8 + 127) / 128 * 128;
+  g.smem_bar = 8 * (2 * NUM_STAGES + 4) + 16 + 128 * 5 * 4 + 64;
+  g.smem_total = g.smem_A + g.smem_stage + g.smem_colinfo + g.smem_table + g.smem_bar + 1024;
+  if (g.smem_total > 227 * 1024) return 0;
+  // the zero-block LBO (a_zero - a) must fit 14 bits of 16-byte units: a_bytes < 256 KB always holds here
+  return 1;
+}
+
+}  // namespace
+
+extern "C" int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes) {
+  UmmaGeom g;
+  uint2 local[MAX_MMAS];
+  return make_geom(C, H, W, k, passes, bank_planes, g, local) ? g.smem_total : 0;
+}
+
+extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
+                                     const void* bank_hi, const void* bank_lo, float bank_scale, const float* pnorm,
+                                     const int32_t* idx, const float* logw, int64_t n_sel, int splits, int passes,
+                                     float* m, float* l, float* acc, float* dbg_dots, void* stream) {
+  UmmaParams p;
+  const int planes = bank_lo ? 2 : 1;
+  if (!make_geom(C, H, W, k, passes, planes, p.g, p.table)) {
+    cds_set_error("cds_els_partials_umma: unsupported geometry C=%d H=%d W=%d k=%d passes=%d planes=%d", C, H, W, k,
+                  passes, planes);
+    return CDS_ERR_UNSUPPORTED;
+  }
+  CDS_CHECK_ARG(B >= 1 && n_sel >= 1 && splits >= 1, "cds_els_partials_umma: empty problem");
+  if (splits > n_sel) splits = (int)n_sel;
+  p.B = B; p.pad = query_pad; p.splits = splits; p.n_sel = n_sel;
+  p.x = x; p.beta = beta;
+  p.bank_hi = (const uint8_t*)bank_hi; p.bank_lo = (const uint8_t*)bank_lo;
+  p.inv_scale = 1.f / bank_scale;
+  p.pnorm = pnorm; p.idx = idx; p.logw = logw;
+  p.m = m; p.l = l; p.acc = acc; p.dbg = dbg_dots;
+  const int tiles = ((H + TI - 1) / TI) * ((W + TJ - 1) / TJ);
+  dim3 grid(tiles, splits, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+#define LAUNCH(CC)                                                                                                  \
+  case CC:                                                                                                          \
+    e = cudaFuncSetAttribute(els_umma_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g.smem_total);     \
+    if (e == cudaSuccess) els_umma_kernel<CC><<<grid, THREADS, p.g.smem_total, st>>>(p);                            \
+    break;
+  switch (C) {
+    LAUNCH(1) LAUNCH(2) LAUNCH(3)
+  }
+#undef LAUNCH
+  if (e != cudaSuccess) {
+    cds_set_error("els_umma_kernel attribute: %s", cudaGetErrorString(e));
+    return CDS_ERR_CUDA;
+  }
+  CDS_CHECK_LAUNCH("els_umma_kernel");
+  return CDS_OK;
+}

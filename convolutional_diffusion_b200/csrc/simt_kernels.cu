@@ -1,0 +1,290 @@
+// Exact fp32 SIMT kernels: unified masked-softmax evaluation of LS / ELS / bbELS, bank preparation
+// (strip8 packing, patch norms), the log-sum-exp merge, the score epilogue and the DDIM update.
+//
+// Reference behaviour restated here (never copied): /root/reference/src/utils/idealscore.py
+//   LS    :497-557   same-location candidates, k x k window of squared differences zero-filled at borders
+//   ELS   :397-473   circular-padded query patches vs every valid (un-padded) patch of every image
+//   bbELS :156-372   zero-padded query; per axis a border query only sees candidates at its own
+//                    coordinate, an interior query sees every interior coordinate
+// All three are  mu = softmax_{cands}( -||q - a p||^2 / (2 beta) + logw_n ) . centre(p).
+#include "common.cuh"
+#include "../../include/cdscore.h"
+
+namespace {
+
+struct SimtParams {
+  int kind, pad, B, C, H, W, k, splits, region;
+  long long n_sel;
+  const float* x;
+  const float* beta;
+  const float* images;
+  const int32_t* idx;
+  const float* logw;
+  float *m, *l, *acc;
+};
+
+constexpr int SIMT_THREADS = 128;
+
+template <int C>
+__global__ void __launch_bounds__(SIMT_THREADS) partials_simt_kernel(SimtParams p) {
+  extern __shared__ float smem[];
+  const int H = p.H, W = p.W, k = p.k, d = k / 2;
+  const int Hp = H + 2 * d, Wp = W + 2 * d, plane = Hp * Wp;
+  float* xs = smem;               // [C][Hp][Wp] padded query
+  float* ts = smem + C * plane;   // [C][Hp][Wp] zero-padded bank image
+  const int b = blockIdx.z, split = blockIdx.y, tid = threadIdx.x;
+  const int pix = blockIdx.x * SIMT_THREADS + tid;
+  bool active = pix < H * W;
+  const int i = active ? pix / W : 0, j = active ? pix % W : 0;
+  if (p.region != 0) {   // 1: only centre pixels, 2: only border pixels (bbELS centre runs on the tensor cores)
+    const bool centre = i >= d && i < H - d && j >= d && j < W - d;
+    active = active && ((p.region == 1) == centre);
+  }
+
+  const float beta = p.beta[b];
+  const float a = sqrtf(1.f - beta);
+  const float sc = -CDS_LOG2E / (2.f * beta);
+  const float* xb = p.x + (size_t)b * C * H * W;
+
+  for (int e = tid; e < C * plane; e += SIMT_THREADS) {
+    int c = e / plane, r = e % plane, y = r / Wp - d, xx = r % Wp - d;
+    float v = 0.f;
+    if (p.pad == CDS_PAD_CIRCULAR) {
+      y = (y % H + H) % H;
+      xx = (xx % W + W) % W;
+      v = xb[(c * H + y) * W + xx];
+    } else if (y >= 0 && y < H && xx >= 0 && xx < W) {
+      v = xb[(c * H + y) * W + xx];
+    }
+    xs[e] = v;
+    ts[e] = 0.f;
+  }
+
+  // candidate ranges in image coordinates (centre of the candidate patch)
+  int u0, u1, v0, v1;
+  if (p.kind == CDS_KIND_LS) {
+    u0 = i; u1 = i + 1; v0 = j; v1 = j + 1;
+  } else if (p.kind == CDS_KIND_ELS) {
+    u0 = d; u1 = H - d; v0 = d; v1 = W - d;
+  } else {
+    const bool rb = (i < d) || (i >= H - d), cb = (j < d) || (j >= W - d);
+    u0 = rb ? i : d; u1 = rb ? i + 1 : H - d;
+    v0 = cb ? j : d; v1 = cb ? j + 1 : W - d;
+  }
+
+  Softmax2<C> sm;
+  sm.init();
+  const long long n0 = p.n_sel * split / p.splits, n1 = p.n_sel * (split + 1) / p.splits;
+  for (long long n = n0; n < n1; ++n) {
+    __syncthreads();
+    const float* img = p.images + (size_t)p.idx[n] * C * H * W;
+    for (int e = tid; e < C * H * W; e += SIMT_THREADS) {
+      int c = e / (H * W), r = e % (H * W), y = r / W, xx = r % W;
+      ts[c * plane + (y + d) * Wp + xx + d] = __ldg(img + e);
+    }
+    __syncthreads();
+    if (!active) continue;
+    const float lw = p.logw[n] * CDS_LOG2E;
+    for (int u = u0; u < u1; ++u) {
+      for (int v = v0; v < v1; ++v) {
+        float dist = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float* xr = xs + c * plane + i * Wp + j;             // top-left of the query patch
+          // padded coordinates: image pixel (y,x) sits at (y+d, x+d), so the patch centred at image (u,v)
+          // starts at padded (u, v)
+          const float* tr = ts + c * plane + u * Wp + v;
+          for (int dy = 0; dy < k; ++dy) {
+            for (int dx = 0; dx < k; ++dx) {
+              float df = fmaf(-a, tr[dy * Wp + dx], xr[dy * Wp + dx]);
+              dist = fmaf(df, df, dist);
+            }
+          }
+        }
+        float val[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) val[c] = ts[c * plane + (u + d) * Wp + v + d];
+        sm.push(fmaf(dist, sc, lw), val);
+      }
+    }
+  }
+  if (active) {
+    const int HW = H * W;
+    const size_t o = ((size_t)split * p.B + b) * HW + pix;
+    p.m[o] = sm.m;
+    p.l[o] = sm.l;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p.acc[(((size_t)split * p.B + b) * C + c) * HW + pix] = sm.acc[c];
+  }
+}
+
+__global__ void pack_strip8_kernel(const float* __restrict__ images, long long N, int C, int H, int W, float scale,
+                                   int plane, uint4* __restrict__ out) {
+  const long long total = N * C * H * W;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int xx = g % W;
+    const int u = (g / W) % H;
+    const long long nc = g / ((long long)W * H);
+    const float* src = images + nc * H * W;
+    __nv_bfloat16 h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = (u + e < H) ? src[(u + e) * W + xx] * scale : 0.f;
+      __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      h[e] = plane == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    out[g] = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+__global__ void patch_norms_kernel(const float* __restrict__ images, long long N, int C, int H, int W, int k,
+                                   float* __restrict__ out) {
+  const int Ph = H - k + 1, Pw = W - k + 1;
+  const long long total = N * Ph * Pw;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int v = g % Pw, u = (g / Pw) % Ph;
+    const long long n = g / ((long long)Pw * Ph);
+    const float* img = images + n * C * H * W;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c)
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+          float t = img[(c * H + u + dy) * W + v + dx];
+          s = fmaf(t, t, s);
+        }
+    out[g] = s;
+  }
+}
+
+__global__ void combine_kernel(const float* __restrict__ m, const float* __restrict__ l, const float* __restrict__ acc,
+                               int S, int B, int C, int HW, float* m_out, float* l_out, float* acc_out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B * HW) return;
+  const int b = g / HW, pix = g % HW;
+  float M = -INFINITY;
+  for (int s = 0; s < S; ++s) M = fmaxf(M, m[((size_t)s * B + b) * HW + pix]);
+  float L = 0.f, A[8];
+  for (int c = 0; c < C; ++c) A[c] = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const size_t o = ((size_t)s * B + b) * HW + pix;
+    const float ms = m[o];
+    const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+    L = fmaf(l[o], w, L);
+    for (int c = 0; c < C; ++c) A[c] = fmaf(acc[(((size_t)s * B + b) * C + c) * HW + pix], w, A[c]);
+  }
+  m_out[(size_t)b * HW + pix] = M;
+  l_out[(size_t)b * HW + pix] = L;
+  for (int c = 0; c < C; ++c) acc_out[((size_t)b * C + c) * HW + pix] = A[c];
+}
+
+__global__ void finalize_kernel(const float* __restrict__ x, const float* __restrict__ beta, const float* __restrict__ l,
+                                const float* __restrict__ acc, int B, int C, int H, int W, int region, int d,
+                                float* __restrict__ mu, float* __restrict__ score) {
+  const int HW = H * W;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B * HW) return;
+  const int b = g / HW, pix = g % HW, i = pix / W, j = pix % W;
+  if (region != 0) {
+    const bool centre = i >= d && i < H - d && j >= d && j < W - d;
+    if ((region == 1) != centre) return;
+  }
+  const float bt = beta[b], a = sqrtf(1.f - bt);
+  const float inv = 1.f / l[(size_t)b * HW + pix];
+  for (int c = 0; c < C; ++c) {
+    const size_t o = ((size_t)b * C + c) * HW + pix;
+    const float mv = acc[o] * inv;
+    if (mu) mu[o] = mv;
+    if (score) score[o] = -(x[o] - a * mv) / bt;
+  }
+}
+
+__global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ cx,
+                                 const float* __restrict__ cmu, int B, long long chw) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= B * chw) return;
+  const int b = g / chw;
+  x[g] = cx[b] * x[g] + cmu[b] * mu[g];
+}
+
+}  // namespace
+
+extern "C" int cds_partials_simt(int kind, int query_pad, const float* x, int B, int C, int H, int W, int k,
+                                 const float* beta, const float* images, const int32_t* idx, const float* logw,
+                                 int64_t n_sel, int splits, int region, float* m, float* l, float* acc,
+                                 void* stream) {
+  CDS_CHECK_ARG(region >= 0 && region <= 2, "cds_partials_simt: bad region %d", region);
+  CDS_CHECK_ARG(kind >= 0 && kind <= 2, "cds_partials_simt: bad kind %d", kind);
+  CDS_CHECK_ARG(C >= 1 && C <= 4, "cds_partials_simt: C=%d unsupported (1..4)", C);
+  CDS_CHECK_ARG(k >= 1 && (k & 1), "cds_partials_simt: k=%d must be odd", k);
+  CDS_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && n_sel >= 1 && splits >= 1, "cds_partials_simt: empty problem");
+  if (kind == CDS_KIND_ELS) CDS_CHECK_ARG(k <= H && k <= W, "cds_partials_simt: ELS needs k <= H,W");
+  if (kind == CDS_KIND_BBELS) CDS_CHECK_ARG(k < H && k < W, "cds_partials_simt: bbELS needs k < H,W (k>=H is LS)");
+  if (splits > n_sel) splits = (int)n_sel;
+  SimtParams p{kind, query_pad, B, C, H, W, k, splits, region, (long long)n_sel, x, beta, images, idx, logw, m, l, acc};
+  const int d = k / 2;
+  const size_t smem = (size_t)2 * C * (H + 2 * d) * (W + 2 * d) * sizeof(float);
+  CDS_CHECK_ARG(smem <= 227 * 1024, "cds_partials_simt: image too large for shared memory (%zu B)", smem);
+  dim3 grid((H * W + SIMT_THREADS - 1) / SIMT_THREADS, splits, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(CC)                                                                                           \
+  case CC:                                                                                                   \
+    cudaFuncSetAttribute(partials_simt_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    partials_simt_kernel<CC><<<grid, SIMT_THREADS, smem, st>>>(p);                                           \
+    break;
+  switch (C) {
+    LAUNCH(1) LAUNCH(2) LAUNCH(3) LAUNCH(4)
+  }
+#undef LAUNCH
+  CDS_CHECK_LAUNCH("partials_simt_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_pack_strip8(const float* images, int64_t N, int C, int H, int W, float scale, int plane,
+                               void* out_bf16, void* stream) {
+  CDS_CHECK_ARG(N >= 1 && C >= 1 && H >= 1 && W >= 1, "cds_pack_strip8: empty bank");
+  const long long total = (long long)N * C * H * W;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads > 148 * 32 ? 148 * 32 : (total + threads - 1) / threads);
+  pack_strip8_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(images, N, C, H, W, scale, plane, (uint4*)out_bf16);
+  CDS_CHECK_LAUNCH("pack_strip8_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_patch_norms(const float* images, int64_t N, int C, int H, int W, int k, float* out, void* stream) {
+  CDS_CHECK_ARG(k >= 1 && k <= H && k <= W, "cds_patch_norms: bad k=%d", k);
+  const long long total = (long long)N * (H - k + 1) * (W - k + 1);
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads > 148 * 32 ? 148 * 32 : (total + threads - 1) / threads);
+  patch_norms_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(images, N, C, H, W, k, out);
+  CDS_CHECK_LAUNCH("patch_norms_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_combine(const float* m, const float* l, const float* acc, int S, int B, int C, int HW, float* m_out,
+                           float* l_out, float* acc_out, void* stream) {
+  CDS_CHECK_ARG(S >= 1 && C <= 8, "cds_combine: bad S=%d C=%d", S, C);
+  const int threads = 128, blocks = (B * HW + threads - 1) / threads;
+  combine_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(m, l, acc, S, B, C, HW, m_out, l_out, acc_out);
+  CDS_CHECK_LAUNCH("combine_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_finalize(const float* x, const float* beta, const float* m, const float* l, const float* acc, int B,
+                            int C, int H, int W, int region, int d, float* mu, float* score, void* stream) {
+  (void)m;
+  const int threads = 128, blocks = (B * H * W + threads - 1) / threads;
+  finalize_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(x, beta, l, acc, B, C, H, W, region, d, mu, score);
+  CDS_CHECK_LAUNCH("finalize_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_ddim_step(float* x, const float* mu, const float* c_x, const float* c_mu, int B, int64_t chw,
+                             void* stream) {
+  const int threads = 256;
+  const long long total = (long long)B * chw;
+  ddim_step_kernel<<<(int)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(x, mu, c_x, c_mu, B, chw);
+  CDS_CHECK_LAUNCH("ddim_step_kernel");
+  return CDS_OK;
+}

@@ -1,0 +1,54 @@
+"""Bank sharding across the GPUs of one box.
+
+The softmax over the bank is associative under (max, sum-exp, weighted-sum), so the training images are split
+across ranks (interleaved, selection.shard) with NO collective on the data path; every rank reduces its slice to
+partials for all B*H*W queries and the only exchange is one small all-gather of those partials per score
+evaluation ((2+C)*B*H*W floats per rank: 20 KB at B=1 CIFAR), followed by the same log-sum-exp merge kernel
+that merges CTA splits (cds_combine).  mu and the DDIM update are then computed redundantly on every rank, which
+keeps x bit-identical across ranks (the merge order is rank order everywhere).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def gather_partials(m, l, acc, group=None):
+    """all-gather of one rank's merged partials: m,l [B,HW], acc [B,C,HW] -> [W,B,HW], [W,B,HW], [W,B,C,HW].
+    Works on any backend (nccl on the GPUs, gloo in the CPU tests)."""
+    world = dist.get_world_size(group)
+    out = []
+    for t in (m, l, acc):
+        t = t.contiguous()
+        g = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(g, t, group=group)
+        out.append(g)
+    return out
+
+
+def allgather_combine(engine, P):
+    """Merge slice 0 of every rank's partials into slice 0 of P, identically on all ranks."""
+    group = engine.group
+    gm, gl, gacc = gather_partials(P.m[0], P.l[0], P.acc[0], group)
+    world = gm.shape[0]
+    _lib.check(engine.lib.cds_combine(_lib.ptr(gm), _lib.ptr(gl), _lib.ptr(gacc), world, P.B, P.C, P.HW,
+                                      _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), _lib.stream_ptr()),
+               "cds_combine")
+    engine.launches += 1
+    return P
+
+
+def init_from_env():
+    """One process per GPU (torchrun): returns (rank, world, local_rank) and initialises NCCL if world > 1."""
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    return rank, world, local

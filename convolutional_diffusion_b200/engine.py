@@ -1,0 +1,176 @@
+"""Launch layer between the Python score modules and the C ABI: picks the kernel for a (kind, geometry),
+sizes the grid against the SM count, owns the partial buffers and runs merge + epilogue.
+
+Everything here is stream ordered on torch's current stream and free of host synchronisation, so a whole
+trajectory can be captured in one CUDA graph (machine.py).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .bank import PatchBank
+
+_SM = {}
+
+
+def sm_count(device):
+    key = torch.device(device).index or 0
+    if key not in _SM:
+        _SM[key] = torch.cuda.get_device_properties(device).multi_processor_count
+    return _SM[key]
+
+
+class Partials:
+    """(m, l, acc) for S slices of B samples (layout in include/cdscore.h)."""
+
+    def __init__(self, S, B, C, HW, device):
+        self.S, self.B, self.C, self.HW = S, B, C, HW
+        self.m = torch.zeros(S, B, HW, dtype=torch.float32, device=device)
+        self.l = torch.zeros(S, B, HW, dtype=torch.float32, device=device)
+        self.acc = torch.zeros(S, B, C, HW, dtype=torch.float32, device=device)
+
+    def packed(self):
+        return torch.cat([self.m[0].reshape(self.B, 1, self.HW), self.l[0].reshape(self.B, 1, self.HW),
+                          self.acc[0]], dim=1)
+
+
+class ScoreEngine:
+    """Evaluates one score module kind against a PatchBank."""
+
+    def __init__(self, bank: PatchBank, precision="bf16x2", use_tensor_cores=True, group=None):
+        self.bank = bank
+        self.lib = bank.lib
+        self.device = bank.device
+        self.precision = precision
+        self.use_tensor_cores = use_tensor_cores
+        self.group = group                       # torch.distributed process group for bank sharding (or None)
+        self._buf = {}
+        self.launches = 0                        # kernels launched through this engine (bench bookkeeping)
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _partials(self, tag, S, B):
+        key = (tag, S, B)
+        if key not in self._buf:
+            self._buf[key] = Partials(S, B, self.bank.C, self.bank.H * self.bank.W, self.device)
+        return self._buf[key]
+
+    def passes_for(self, k, beta_min):
+        if self.precision == "bf16":
+            return 1
+        if self.precision == "bf16x2":
+            return 2
+        # "auto": one bf16 pass when the logit error it causes stays below ~1e-2
+        d = k * k * self.bank.C
+        a_over_b = (max(1.0 - beta_min, 0.0) ** 0.5) / max(beta_min, 1e-6)
+        return 1 if a_over_b * (d ** 0.5) * 2.0 ** -9 < 1e-2 else 2
+
+    def umma_supported(self, k, passes):
+        b = self.bank
+        if not self.use_tensor_cores:
+            return False
+        planes = 1 if b.strip8()[1] is None else 2
+        return self.lib.cds_els_umma_smem_bytes(b.C, b.H, b.W, k, passes, planes) > 0
+
+    def _splits(self, tiles, B, n_sel, waves=1):
+        ctas = max(1, tiles * B)
+        s = max(1, (sm_count(self.device) * waves) // ctas)
+        return int(min(s, n_sel))
+
+    # ---- kernels -------------------------------------------------------------------------------
+    def simt_partials(self, kind, pad, x, beta, k, sel, region=0, tag="simt"):
+        idx, logw, n_sel = sel
+        b = self.bank
+        B = x.shape[0]
+        tiles = (b.H * b.W + 127) // 128
+        S = self._splits(tiles, B, n_sel, waves=4)
+        P = self._partials(tag, S, B)
+        _lib.check(self.lib.cds_partials_simt(_lib.KIND[kind], _lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k,
+                                              _lib.ptr(beta), _lib.ptr(b.images), _lib.ptr(idx), _lib.ptr(logw),
+                                              n_sel, S, region, _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc),
+                                              _lib.stream_ptr()), "cds_partials_simt")
+        self.launches += 1
+        return P
+
+    def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma"):
+        idx, logw, n_sel = sel
+        b = self.bank
+        B = x.shape[0]
+        hi, lo, scale = b.strip8()
+        pn = b.patch_norms(k)
+        tiles = ((b.H + 15) // 16) * ((b.W + 7) // 8)
+        S = self._splits(tiles, B, n_sel)
+        P = self._partials(tag, S, B)
+        _lib.check(self.lib.cds_els_partials_umma(_lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta),
+                                                  _lib.ptr(hi), _lib.ptr(lo), scale, _lib.ptr(pn), _lib.ptr(idx),
+                                                  _lib.ptr(logw), n_sel, S, passes, _lib.ptr(P.m), _lib.ptr(P.l),
+                                                  _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr()),
+                   "cds_els_partials_umma")
+        self.launches += 1
+        return P
+
+    def combine(self, P):
+        """Merge the S slices into slice 0 (in place), then across ranks when the bank is sharded."""
+        if P.S > 1:
+            _lib.check(self.lib.cds_combine(_lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), P.S, P.B, P.C, P.HW,
+                                            _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), _lib.stream_ptr()),
+                       "cds_combine")
+            self.launches += 1
+        if self.group is not None:
+            from .distributed import allgather_combine
+            allgather_combine(self, P)
+        return P
+
+    def finalize(self, P, x, beta, mu, score, region=0, d=0):
+        b = self.bank
+        _lib.check(self.lib.cds_finalize(_lib.ptr(x), _lib.ptr(beta), _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc),
+                                         x.shape[0], b.C, b.H, b.W, region, d, _lib.ptr(mu), _lib.ptr(score),
+                                         _lib.stream_ptr()), "cds_finalize")
+        self.launches += 1
+
+    def ddim_step(self, x, mu, c_x, c_mu):
+        B = x.shape[0]
+        _lib.check(self.lib.cds_ddim_step(_lib.ptr(x), _lib.ptr(mu), _lib.ptr(c_x), _lib.ptr(c_mu), B,
+                                          x.numel() // B, _lib.stream_ptr()), "cds_ddim_step")
+        self.launches += 1
+
+    # ---- one score evaluation ------------------------------------------------------------------
+    def evaluate(self, kind, x, beta, k, sel, query_pad=None, mu=None, score=None, beta_min=None, sel_ls=None):
+        """x [B,C,H,W] fp32 on device, beta [B] fp32 on device.  Writes mu and/or score (allocated if None
+        and requested by passing an empty tensor); returns (mu, score)."""
+        b = self.bank
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert tuple(x.shape[1:]) == (b.C, b.H, b.W), f"x {tuple(x.shape)} does not match bank {(b.C, b.H, b.W)}"
+        if k % 2 == 0 or k < 1:
+            raise ValueError(f"kernel size must be odd and positive, got {k}")
+        if beta_min is None:
+            beta_min = float(beta.min())         # host sync; the machine passes beta_min explicitly
+        if kind == "bbELS" and k >= b.H:          # idealscore.py:163-164: delegate to the internal LS module
+            kind, sel = "LS", (sel_ls if sel_ls is not None else sel)
+        if kind == "LS":
+            P = self.combine(self.simt_partials("LS", "zeros", x, beta, k, sel))
+            self.finalize(P, x, beta, mu, score)
+        elif kind == "ELS":
+            if k > b.H or k > b.W:
+                raise ValueError(f"ELS needs kernel size <= image size, got k={k} for {b.H}x{b.W}")
+            pad = query_pad or "circular"
+            passes = self.passes_for(k, beta_min)
+            if self.umma_supported(k, passes):
+                P = self.umma_partials(pad, x, beta, k, sel, passes)
+            else:
+                P = self.simt_partials("ELS", pad, x, beta, k, sel)
+            self.finalize(self.combine(P), x, beta, mu, score)
+        elif kind == "bbELS":
+            passes = self.passes_for(k, beta_min)
+            d = k // 2
+            if self.umma_supported(k, passes):
+                Pc = self.combine(self.umma_partials("zeros", x, beta, k, sel, passes))
+                Pb = self.combine(self.simt_partials("bbELS", "zeros", x, beta, k, sel, region=2, tag="border"))
+                self.finalize(Pc, x, beta, mu, score, region=1, d=d)
+                self.finalize(Pb, x, beta, mu, score, region=2, d=d)
+            else:
+                P = self.combine(self.simt_partials("bbELS", "zeros", x, beta, k, sel))
+                self.finalize(P, x, beta, mu, score)
+        else:
+            raise ValueError(f"unknown score module kind {kind!r}")
+        return mu, score

@@ -1,0 +1,152 @@
+"""ScheduledScoreMachine: the deterministic DDIM reverse loop that drives the score modules.
+
+Mirrors `/root/reference/src/utils/idealscore.py:55-124` (constructor, forward, sample):
+    for i = nsteps-1 ... 1:  t = i/nsteps, k = scales[i], s = backbone(t, x, label, device, k),
+                             eps = -sqrt(beta_t) s,  x <- sqrt(a'/a) x + (sqrt(b') - sqrt(a'/a) sqrt(b)) eps
+With one of this package's score modules as backbone the loop runs entirely on the device: each step is
+[partials kernel(s) -> merge -> epilogue -> fused DDIM update in terms of the denoised estimate
+x <- sqrt(b'/b) x + (sqrt(a') - sqrt(b'/b) sqrt(a)) mu], and the whole trajectory is captured once per
+(scales, batch, label) in a CUDA graph and replayed.  Any other callable backbone takes the generic loop.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .modules import _ScoreModuleBase, _as_label, cosine_noise_schedule
+
+
+def ddim_coefficients(nsteps, schedule=cosine_noise_schedule):
+    """Per step i = nsteps-1 ... 1: (i, beta_t, c_x, c_mu) of  x <- c_x x + c_mu mu  (idealscore.py:88-116)."""
+    out = []
+    for i in range(nsteps - 1, 0, -1):
+        t = torch.tensor([i / nsteps], dtype=torch.float32)
+        bt = float(schedule(t))
+        bp = max(float(schedule(t - 1 / nsteps)), 0.0)
+        r = math.sqrt(bp / bt)
+        out.append((i, bt, r, math.sqrt(1.0 - bp) - r * math.sqrt(1.0 - bt)))
+    return out
+
+
+class ScheduledScoreMachine(nn.Module):
+    def __init__(self, backbone, in_channels=3, imsize=32, default_time_steps=20,
+                 noise_schedule=cosine_noise_schedule, score_backbone=True, scales=None, use_cuda_graph=True,
+                 **kwargs):
+        super().__init__()
+        self.backbone = backbone
+        self.default_time_steps = default_time_steps
+        self.noise_schedule = noise_schedule
+        self.in_channels = in_channels
+        self.imsize = imsize
+        self.score_backbone = score_backbone
+        self.scales = scales
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x, nsteps=None, label=None, device=None, visualize=False):
+        if device is None:
+            device = torch.device("cuda")
+        if nsteps is None:
+            nsteps = self.default_time_steps if self.scales is None else len(self.scales)
+        native = isinstance(self.backbone, _ScoreModuleBase) and self.score_backbone \
+            and self.backbone.schedule is self.noise_schedule
+        if native:
+            return self._forward_native(x, nsteps, _as_label(label), torch.device(device))
+        return self._forward_generic(x, nsteps, label, device)
+
+    def sample(self, nsteps=None, label=None, device=None):
+        if device is None:
+            device = torch.device("cuda")
+        x = torch.randn(1, self.in_channels, self.imsize, self.imsize, device=device)
+        return self(x.clone(), nsteps=nsteps, label=label, device=device)
+
+    # ---- generic loop: any callable backbone, same arithmetic as the reference --------------------
+    def _forward_generic(self, x, nsteps, label, device):
+        x = x.clone()
+        for i in range(nsteps - 1, 0, -1):
+            bsz = x.shape[0]
+            t = i * torch.ones(bsz) / nsteps
+            beta_t = self.noise_schedule(t).to(device)
+            k = None if self.scales is None else self.scales[i]
+            if label is not None:
+                eps = self.backbone(t, x, label=label, device=device, k=k)
+            else:
+                eps = self.backbone(t, x, device=device, k=k)
+            if self.score_backbone:
+                eps = eps * (-beta_t ** 0.5)[:, None, None, None]
+            alpha_t = 1 - beta_t
+            beta_prev = self.noise_schedule(t - 1 / nsteps).to(device)
+            alpha_prev = 1 - beta_prev
+            ratio = ((alpha_prev / alpha_t) ** 0.5)[:, None, None, None]
+            x = x * ratio + (beta_prev[:, None, None, None] ** 0.5 - ratio * beta_t[:, None, None, None] ** 0.5) * eps
+        return x
+
+    # ---- native loop: device resident, graph captured ----------------------------------------------
+    def _plan(self, nsteps, B, device):
+        mod = self.backbone
+        steps = []
+        for i, bt, cx, cmu in ddim_coefficients(nsteps, self.noise_schedule):
+            k = mod.kernel_size if self.scales is None else int(self.scales[i])
+            steps.append(dict(i=i, k=k, beta=bt,
+                              beta_dev=torch.full((B,), bt, dtype=torch.float32, device=device),
+                              cx=torch.full((B,), cx, dtype=torch.float32, device=device),
+                              cmu=torch.full((B,), cmu, dtype=torch.float32, device=device)))
+        return steps
+
+    def _run_steps(self, eng, steps, x, mu, sel, sel_ls, record=None):
+        mod = self.backbone
+        for st in steps:
+            eng.evaluate(mod.kind, x, st["beta_dev"], st["k"], sel, query_pad=mod.query_pad, mu=mu, score=None,
+                         beta_min=st["beta"], sel_ls=sel_ls)
+            if record is not None:
+                record.append(dict(i=st["i"], k=st["k"], beta=st["beta"], x=x.clone(), mu=mu.clone()))
+            eng.ddim_step(x, mu, st["cx"], st["cmu"])
+
+    def _forward_native(self, x, nsteps, label, device, record=None):
+        mod = self.backbone
+        eng = mod.engine(device)
+        B = x.shape[0]
+        sel = mod.selection(label)
+        needs_ls = mod.kind == "bbELS" and any(
+            (mod.kernel_size if self.scales is None else int(s)) >= eng.bank.H
+            for s in (self.scales[1:nsteps] if self.scales is not None else [mod.kernel_size]))
+        sel_ls = mod.selection(label, kind="LS") if needs_ls else None
+        shuffled = mod.shuffle or (mod.kind == "LS" and mod._ls_shuffles()) or needs_ls and mod._ls_shuffles()
+        key = (nsteps, B, label, tuple(self.scales) if self.scales is not None else None)
+        with torch.cuda.device(eng.device):
+            if record is not None or not self.use_cuda_graph or shuffled or eng.group is not None:
+                xw = x.to(eng.device, torch.float32).clone().contiguous()
+                mu = torch.empty_like(xw)
+                self._run_steps(eng, self._plan(nsteps, B, eng.device), xw, mu, sel, sel_ls, record)
+                return xw
+            if key not in self._graphs:
+                steps = self._plan(nsteps, B, eng.device)
+                xs = torch.zeros(B, eng.bank.C, eng.bank.H, eng.bank.W, dtype=torch.float32, device=eng.device)
+                mu = torch.empty_like(xs)
+                eng.bank.strip8()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):            # warm-up: lazy bank layouts, smem attributes
+                    self._run_steps(eng, steps, xs, mu, sel, sel_ls)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._run_steps(eng, steps, xs, mu, sel, sel_ls)
+                self._graphs[key] = (graph, xs, mu, steps, sel, sel_ls)
+            graph, xs, mu, *_ = self._graphs[key]
+            xs.copy_(x.to(eng.device, torch.float32))
+            graph.replay()
+            return xs.clone()
+
+    def trajectory(self, x, nsteps=None, label=None, device=None):
+        """Runs the native loop eagerly and returns (final x, per-step records of x / mu) -- used by the parity
+        tests, which check the denoised estimate at every step."""
+        if nsteps is None:
+            nsteps = self.default_time_steps if self.scales is None else len(self.scales)
+        rec = []
+        out = self._forward_native(x, nsteps, _as_label(label), torch.device(device or "cuda"), record=rec)
+        return out, rec

@@ -1,0 +1,164 @@
+"""Drop-in score modules with the reference's constructor and call signatures.
+
+Mirrors `/root/reference/src/utils/idealscore.py`:
+    LocalScoreModule              :476   LS
+    LocalEquivScoreModule         :375   ELS
+    LocalEquivBordersScoreModule  :127   bbELS
+    cosine_noise_schedule / exponential_schedule / linear_noise_schedule  :41-52
+call protocol (idealscore.py:97,99; scripts/scales_calibration.py:151):
+    module(t, x, label=None, device=None, k=None) -> score tensor, same shape as x
+The bodies are not the reference's: the bank is uploaded once (bank.PatchBank) and each call launches the
+sm_100a kernels behind include/cdscore.h.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .bank import PatchBank, dataset_to_tensors
+from .engine import ScoreEngine
+from .selection import dataloader_shuffle_order
+
+
+def exponential_schedule(t):
+    return 1 - torch.exp(-2 * t)
+
+
+def linear_noise_schedule(t):
+    return 0.01 + 0.97 * t
+
+
+def cosine_noise_schedule(t, mode="legacy"):
+    """beta(t), the noise variance (noise_schedules.py:15-18)."""
+    if mode == "legacy":
+        return 1 - torch.cos(t / 1.008 * math.pi / 2) ** 2
+    return 1 - torch.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+
+
+def _as_label(label):
+    if label is None:
+        return None
+    if torch.is_tensor(label):
+        return int(label.reshape(-1)[0].item())
+    return int(label)
+
+
+class _ScoreModuleBase(nn.Module):
+    kind = None
+    query_pad = None
+
+    def __init__(self, dataset, kernel_size, batch_size, image_size, schedule, max_samples, shuffle,
+                 precision="bf16x2", use_tensor_cores=True, process_group=None, bank=None):
+        super().__init__()
+        self.dataset = dataset
+        self.batch_size = batch_size
+        self.kernel_size = kernel_size
+        self.image_size = image_size
+        self.schedule = schedule
+        self.max_samples = max_samples
+        self.shuffle = shuffle
+        self.precision = precision
+        self.use_tensor_cores = use_tensor_cores
+        self.process_group = process_group
+        self._bank = bank
+        self._engine = None
+
+    # -- lazily built device state ----------------------------------------------------------------
+    def engine(self, device=None) -> ScoreEngine:
+        if self._engine is None:
+            if self._bank is None:
+                images, labels = dataset_to_tensors(self.dataset)
+                self._bank = PatchBank(images, labels, device=device)
+            self._engine = ScoreEngine(self._bank, precision=self.precision,
+                                       use_tensor_cores=self.use_tensor_cores, group=self.process_group)
+        return self._engine
+
+    @property
+    def bank(self):
+        return self.engine().bank
+
+    def _rank_world(self):
+        if self.process_group is None:
+            return 0, 1
+        import torch.distributed as dist
+        return dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+
+    def selection(self, label, kind=None):
+        kind = kind or self.kind
+        eng = self.engine()
+        order = None
+        if self.shuffle or kind == "LS" and self._ls_shuffles():
+            order = dataloader_shuffle_order(eng.bank.N)
+        rank, world = self._rank_world()
+        return eng.bank.selection(kind, label, self.batch_size, self.max_samples, order, rank, world)
+
+    def _ls_shuffles(self):
+        """LS hard-codes shuffle=True (idealscore.py:489); the order only matters when batches end up with
+        unequal post-filter sizes, so skip the permutation when a single batch covers the bank."""
+        return self.batch_size < len(self.dataset)
+
+    def betas(self, t, device):
+        return self.schedule(torch.as_tensor(t, dtype=torch.float32).reshape(-1).cpu()).to(device, torch.float32)
+
+    def forward(self, t, x, label=None, device=None, k=None):
+        if device is None:
+            device = torch.device("cuda")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("the B200 score modules run on CUDA only (no CPU fallback)")
+        eng = self.engine(device)
+        k = self.kernel_size if k is None else int(k)
+        xd = x.to(eng.device, torch.float32).contiguous()
+        tt = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+        if tt.numel() == 1 and xd.shape[0] > 1:
+            tt = tt.expand(xd.shape[0])
+        beta_cpu = self.schedule(tt.cpu().float())
+        beta = beta_cpu.to(eng.device, torch.float32).contiguous()
+        lab = _as_label(label)
+        sel = self.selection(lab)
+        sel_ls = None
+        if self.kind == "bbELS" and k >= xd.shape[-2]:
+            sel_ls = self.selection(lab, kind="LS")
+        score = torch.empty_like(xd)
+        eng.evaluate(self.kind, xd, beta, k, sel, query_pad=self.query_pad, mu=None, score=score,
+                     beta_min=float(beta_cpu.min()), sel_ls=sel_ls)
+        return score
+
+
+class LocalScoreModule(_ScoreModuleBase):
+    """LS (idealscore.py:476-557).  Note the reference default schedule is the exponential one (:484)."""
+    kind = "LS"
+
+    def __init__(self, dataset, kernel_size=3, image_size=32, batch_size=256, show_plots=False,
+                 schedule=exponential_schedule, max_samples=None, **kwargs):
+        super().__init__(dataset, kernel_size, batch_size, image_size, schedule, max_samples, shuffle=False, **_own(kwargs))
+        self.show_plots = show_plots
+
+
+class LocalEquivScoreModule(_ScoreModuleBase):
+    """ELS (idealscore.py:375-473): circular-padded query, every valid patch of every image."""
+    kind = "ELS"
+    query_pad = "circular"
+
+    def __init__(self, dataset, kernel_size=3, batch_size=64, image_size=32, channels=3,
+                 schedule=cosine_noise_schedule, max_samples=None, shuffle=False, query_pad="circular", **kwargs):
+        super().__init__(dataset, kernel_size, batch_size, image_size, schedule, max_samples, shuffle, **_own(kwargs))
+        self.channels = channels
+        self.query_pad = query_pad       # "zeros" = the zero-padded ELS variant of BASELINE config 2
+
+
+class LocalEquivBordersScoreModule(_ScoreModuleBase):
+    """bbELS (idealscore.py:127-372): zero-padded query, border-aware candidate sets; k >= H -> LS (:163)."""
+    kind = "bbELS"
+    query_pad = "zeros"
+
+    def __init__(self, dataset, kernel_size=3, batch_size=64, image_size=32, channels=3,
+                 schedule=cosine_noise_schedule, max_samples=None, shuffle=False, **kwargs):
+        super().__init__(dataset, kernel_size, batch_size, image_size, schedule, max_samples, shuffle, **_own(kwargs))
+        self.channels = channels
+
+
+def _own(kwargs):
+    return {k: kwargs[k] for k in ("precision", "use_tensor_cores", "process_group", "bank") if k in kwargs}

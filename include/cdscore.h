@@ -1,0 +1,96 @@
+/* cdscore.h -- C ABI of the B200-native analytic score machines (LS / ELS / bbELS).
+ *
+ * This is the drop-in boundary.  The reference (henhen724/convolutional_diffusion) has no FFI: its
+ * hot path is the Python callable  module(t, x, label=None, device=None, k=None)  defined in
+ * src/utils/idealscore.py (LS :497, ELS :397, bbELS :156) and the DDIM loop :76-118.  Every entry
+ * point below replaces one stage of that callable's body; the Python host in
+ * convolutional_diffusion_b200/ re-assembles them behind the reference's signatures.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless named *_host
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream ordered, never synchronises,
+ *     and is CUDA-graph capturable
+ *   - return value 0 = ok; otherwise a negative code, text via cds_last_error()
+ *   - images are planar fp32 [N][C][H][W] in [-1,1]; x / outputs are planar fp32 [B][C][H][W]
+ *   - "partials" are the flash-softmax triple per sample and query pixel:
+ *        m   [S][B][H*W]      running max of the logits seen
+ *        l   [S][B][H*W]      sum exp(logit - m)
+ *        acc [S][B][C][H*W]   sum exp(logit - m) * centre pixel of the candidate patch
+ *     S = number of independent bank slices (CTA splits here, GPUs after the all-gather)
+ */
+#ifndef CDSCORE_H
+#define CDSCORE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDS_KIND_LS    0   /* idealscore.py:476  LocalScoreModule              */
+#define CDS_KIND_ELS   1   /* idealscore.py:375  LocalEquivScoreModule         */
+#define CDS_KIND_BBELS 2   /* idealscore.py:127  LocalEquivBordersScoreModule  */
+#define CDS_PAD_ZEROS    0 /* F.pad(value=0)          idealscore.py:171 */
+#define CDS_PAD_CIRCULAR 1 /* F.pad(mode='circular')  idealscore.py:414 */
+
+int         cds_abi_version(void);
+const char* cds_last_error(void);
+/* SM count / compute capability of the current device (for grid sizing on the host side) */
+int         cds_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- bank preparation (once per bank; replaces the per-call DataLoader pass, idealscore.py:184,430,521) */
+
+/* Pack planar fp32 images into the tensor-core streaming layout "strip8":
+ *   out[n][c][u][x][8] (bf16), element e = scale * img[n][c][u+e][x]  (0 beyond the last row).
+ * One 16-byte granule = an 8-pixel vertical strip, so a k x k patch row block is addressable with
+ * 16-byte-stride UMMA descriptors (implicit im2col; patches are never materialised).
+ * plane = 0: bf16(scale*v);  plane = 1: bf16 of the rounding residual (second plane for non-8-bit banks). */
+int cds_pack_strip8(const float* images, int64_t N, int C, int H, int W, float scale, int plane,
+                    void* out_bf16, void* stream);
+
+/* ||p||^2 of every valid (un-padded) k x k x C patch: out[n][H-k+1][W-k+1]  (idealscore.py:451,243) */
+int cds_patch_norms(const float* images, int64_t N, int C, int H, int W, int k, float* out, void* stream);
+
+/* ---- score partials (the hot path) */
+
+/* Exact fp32 SIMT evaluation of the unified masked-softmax form for LS / ELS / bbELS.
+ * idx[n_sel] selects bank images (class filter / max_samples, resolved on the host),
+ * logw[n_sel] is the per-image log-weight (the reference's per-batch mean, idealscore.py:470,553).
+ * region: 0 = every query pixel, 1 = only centre pixels (d<=i<H-d, d<=j<W-d), 2 = only border pixels;
+ * pixels outside the region are left untouched in m/l/acc.  m is in log2 units. */
+int cds_partials_simt(int kind, int query_pad, const float* x, int B, int C, int H, int W, int k,
+                      const float* beta, const float* images, const int32_t* idx, const float* logw,
+                      int64_t n_sel, int splits, int region, float* m, float* l, float* acc, void* stream);
+
+/* tcgen05 / TMEM evaluation of ELS (and the bbELS centre region): queries = all H*W pixels of x padded
+ * per query_pad, candidates = every valid k x k patch of the selected images, streamed from the strip8
+ * bank by bulk-async copies.  passes = 1: bf16 query; 2: bf16 hi+lo query (fp32-grade dot products for
+ * 8-bit banks).  bank_lo may be NULL (8-bit-exact bank).  dbg_dots: optional [B][H*W][P] raw dot dump of the
+ * first selected image (tests only, may be NULL). */
+int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k,
+                          const float* beta, const void* bank_hi, const void* bank_lo, float bank_scale,
+                          const float* pnorm, const int32_t* idx, const float* logw, int64_t n_sel,
+                          int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
+                          void* stream);
+/* dynamic shared memory the umma kernel needs for this geometry (0 = unsupported geometry) */
+int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes);
+
+/* ---- merge + epilogue */
+
+/* log-sum-exp merge of S slices into slice 0 of (m_out,l_out,acc_out) (may alias the inputs) */
+int cds_combine(const float* m, const float* l, const float* acc, int S, int B, int C, int HW,
+                float* m_out, float* l_out, float* acc_out, void* stream);
+
+/* mu = acc/l ; score = -(x - sqrt(1-beta) mu)/beta  (idealscore.py:372,473,557).
+ * region: 0 = all pixels, 1 = only pixels with d<=i<H-d and d<=j<W-d (bbELS centre), 2 = the complement. */
+int cds_finalize(const float* x, const float* beta, const float* m, const float* l, const float* acc,
+                 int B, int C, int H, int W, int region, int d, float* mu, float* score, void* stream);
+
+/* one deterministic DDIM update of ScheduledScoreMachine.forward (idealscore.py:101-116) written in terms
+ * of the denoised estimate:  x <- c_x[b]*x + c_mu[b]*mu  */
+int cds_ddim_step(float* x, const float* mu, const float* c_x, const float* c_mu, int B, int64_t chw,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,224 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference-generated goldens.
+
+Tolerances (BASELINE.json north_star): denoised estimate mu max-abs <= 1e-3 on [-1,1] images at every step;
+final sample PSNR >= 50 dB against the reference trajectory from the same seed.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_case
+
+pytestmark = pytest.mark.gpu
+
+MU_TOL = 1e-3
+
+
+def _mods():
+    import convolutional_diffusion_b200 as cd
+    return cd
+
+
+def _dataset(bank, labels):
+    return (torch.from_numpy(np.asarray(bank)).float(), torch.from_numpy(np.asarray(labels)).long())
+
+
+def _make(kind, ds, k, bs, ms, **kw):
+    cd = _mods()
+    cls = {"ELS": cd.LocalEquivScoreModule, "bbELS": cd.LocalEquivBordersScoreModule, "LS": cd.LocalScoreModule}[kind]
+    return cls(ds, kernel_size=k, batch_size=bs, max_samples=ms, schedule=cd.cosine_noise_schedule, **kw)
+
+
+def _mu_from_score(score, x, beta):
+    return (score * beta + x) / math.sqrt(1 - beta)
+
+
+@pytest.mark.parametrize("tc", [True, False], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("path", golden_files("module"), ids=os.path.basename)
+def test_module_golden(path, tc):
+    from oracle import score_oracle as so
+    c = load_case(path)
+    kind = str(c["kind"])
+    label = None if int(c["label"]) < 0 else int(c["label"])
+    ms = None if int(c["max_samples"]) < 0 else int(c["max_samples"])
+    k = int(c["k"])
+    torch.manual_seed(0)
+    mod = _make(kind, _dataset(c["bank"], c["labels"]), k, int(c["batch_size"]), ms, use_tensor_cores=tc)
+    x = torch.from_numpy(c["x"]).cuda()
+    t = torch.tensor([float(c["t"])])
+    lab = None if label is None else torch.tensor([label])
+    s = mod(t, x, label=lab, device=torch.device("cuda"))
+    assert s.shape == x.shape and s.dtype == torch.float32 and s.is_cuda
+    beta = float(so.cosine_beta(float(c["t"])))
+    mu = _mu_from_score(s.cpu().double().numpy()[0], c["x"][0].astype(np.float64), beta)
+    mu_ref = _mu_from_score(c["score"][0].astype(np.float64), c["x"][0].astype(np.float64), beta)
+    err = np.max(np.abs(mu - mu_ref))
+    assert err < MU_TOL, f"mu max-abs error {err:.3e} vs reference"
+    # and against the float64 oracle
+    h = c["x"].shape[-1]
+    sel_kind = "LS" if (kind == "bbELS" and k >= h) else kind
+    idx, logw = so.select_bank(sel_kind, c["labels"], label, int(c["batch_size"]), ms)
+    _, mu_o = so.score(kind, c["x"][0], c["bank"][idx], beta, k, logw)
+    assert np.max(np.abs(mu - mu_o)) < MU_TOL
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
+@pytest.mark.parametrize("path", golden_files("machine"), ids=os.path.basename)
+def test_machine_golden(path, graph):
+    cd = _mods()
+    c = load_case(path)
+    kind = str(c["kind"])
+    label = None if int(c["label"]) < 0 else int(c["label"])
+    scales = [int(v) for v in c["scales"]]
+    torch.manual_seed(0)
+    mod = _make(kind, _dataset(c["bank"], c["labels"]), 3, int(c["batch_size"]), None)
+    machine = cd.ScheduledScoreMachine(mod, in_channels=c["x"].shape[1], imsize=c["x"].shape[-1], scales=scales,
+                                       use_cuda_graph=graph)
+    x = torch.from_numpy(c["x"]).cuda()
+    lab = None if label is None else torch.tensor([label])
+    out = machine(x.clone(), label=lab, device=torch.device("cuda"))
+    if graph:                                         # replay must reproduce the first run bit for bit
+        out2 = machine(x.clone(), label=lab, device=torch.device("cuda"))
+        assert torch.equal(out, out2)
+    ref = c["out"].astype(np.float64)
+    got = out.cpu().double().numpy()
+    mse = np.mean((got - ref) ** 2)
+    psnr = 10 * np.log10(4.0 / max(mse, 1e-30))
+    assert psnr >= 50.0, psnr
+    assert np.max(np.abs(got - ref)) < 2e-3
+
+
+def _oracle_mu(kind, x, bank, labels, label, beta, k, bs, ms=None):
+    from oracle import score_oracle as so
+    h = x.shape[-1]
+    sel_kind = "LS" if (kind == "bbELS" and k >= h) else kind
+    idx, logw = so.select_bank(sel_kind, labels, label, bs, ms)
+    return so.score(kind, x, bank[idx], beta, k, logw)[1]
+
+
+@pytest.mark.parametrize("kind,C,H,N,k,t,label,bs", [
+    ("ELS", 3, 32, 48, 3, 0.10, None, 16),
+    ("ELS", 3, 32, 48, 9, 0.50, 2, 16),
+    ("ELS", 3, 32, 40, 17, 0.90, None, 64),
+    ("ELS", 1, 32, 64, 5, 0.25, None, 24),
+    ("ELS", 1, 28, 40, 15, 0.85, 1, 16),
+    ("bbELS", 3, 32, 32, 5, 0.25, None, 16),
+    ("bbELS", 3, 32, 24, 17, 0.90, 3, 8),
+    ("bbELS", 1, 32, 32, 11, 0.60, None, 16),
+    ("LS", 1, 28, 512, 5, 0.40, None, 512),
+    ("LS", 3, 32, 256, 7, 0.70, 4, 256),
+])
+def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs):
+    """CIFAR / MNIST geometries at bank sizes the float64 oracle finishes in seconds."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
+    bank, labels = synthetic_bank(N, C, H, nlabels=5, seed=11)
+    beta = float(so.cosine_beta(t))
+    B = 2
+    x = noisy_query(bank, beta, B, seed=5)
+    mod = _make(kind, (bank, labels), k, bs, None)
+    lab = None if label is None else torch.tensor([label])
+    s = mod(torch.full((B,), t), x.cuda(), label=lab, device=torch.device("cuda")).cpu().double().numpy()
+    for b in range(B):                                 # B samples == B independent b=1 reference calls
+        mu = _mu_from_score(s[b], x[b].double().numpy(), beta)
+        mu_o = _oracle_mu(kind, x[b].numpy(), bank.numpy(), labels.numpy(), label, beta, k, bs)
+        assert np.max(np.abs(mu - mu_o)) < MU_TOL, (b, np.max(np.abs(mu - mu_o)))
+
+
+def test_non8bit_bank_uses_residual_plane():
+    """A bank that is not on the 8-bit grid needs the second bf16 plane to stay within tolerance."""
+    from oracle import score_oracle as so
+    g = torch.Generator().manual_seed(3)
+    bank = torch.rand(24, 3, 16, 16, generator=g) * 2 - 1
+    labels = torch.zeros(24, dtype=torch.long)
+    beta = float(so.cosine_beta(0.3))
+    x = math.sqrt(1 - beta) * bank[:1] + math.sqrt(beta) * torch.randn(1, 3, 16, 16, generator=g)
+    mod = _make("ELS", (bank, labels), 5, 8, None)
+    assert mod.bank.strip8()[1] is not None
+    s = mod(torch.tensor([0.3]), x.cuda(), device=torch.device("cuda")).cpu().double().numpy()[0]
+    mu = _mu_from_score(s, x[0].double().numpy(), beta)
+    mu_o = _oracle_mu("ELS", x[0].numpy(), bank.numpy(), labels.numpy(), None, beta, 5, 8)
+    assert np.max(np.abs(mu - mu_o)) < MU_TOL
+
+
+# ---- size-independent properties at full bank size ------------------------------------------------------
+@pytest.fixture(scope="module")
+def cifar_bank():
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    return synthetic_bank(50000, 3, 32, nlabels=10, seed=0)
+
+
+def test_full_bank_els_shift_equivariance(cifar_bank):
+    """ELS with circular padding commutes with circular shifts of x (full 50k bank, class conditional)."""
+    bank, labels = cifar_bank
+    mod = _make("ELS", (bank, labels), 7, 64, None)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 3, 32, 32, generator=g).cuda()
+    lab = torch.tensor([3])
+    t = torch.tensor([0.45])
+    s0 = mod(t, x, label=lab, device=torch.device("cuda"))
+    s1 = mod(t, torch.roll(x, (5, 11), dims=(2, 3)), label=lab, device=torch.device("cuda"))
+    assert torch.allclose(torch.roll(s0, (5, 11), dims=(2, 3)), s1, atol=2e-3)
+
+
+def test_full_bank_split_invariance(cifar_bank):
+    """The (max, sum-exp, weighted-sum) merge is associative: one slice vs many slices of the bank."""
+    cd = _mods()
+    bank, labels = cifar_bank
+    mod = _make("ELS", (bank, labels), 5, 64, None)
+    eng = mod.engine("cuda")
+    x = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(4)).cuda()
+    beta = torch.tensor([0.3], device="cuda")
+    sel = mod.selection(7)
+    outs = []
+    for waves in (1, 3):
+        eng._splits_orig = eng._splits
+        eng._splits = lambda tiles, B, n_sel, waves_=waves, **kw: max(1, min(n_sel, 18 * waves_))
+        mu = torch.empty_like(x)
+        eng.evaluate("ELS", x, beta, 5, sel, query_pad="circular", mu=mu, beta_min=0.3)
+        outs.append(mu.clone())
+        eng._splits = eng._splits_orig
+    assert torch.allclose(outs[0], outs[1], atol=1e-5)
+
+
+def test_full_bank_ls_equals_bbels_when_k_ge_h():
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    bank, labels = synthetic_bank(2000, 1, 28, nlabels=10, seed=2)
+    x = torch.randn(1, 1, 28, 28, generator=torch.Generator().manual_seed(1)).cuda()
+    t = torch.tensor([0.5])
+    ls = _make("LS", (bank, labels), 29, 2000, None)
+    bb = _make("bbELS", (bank, labels), 29, 2000, None)
+    assert torch.allclose(ls(t, x, device=torch.device("cuda"), k=29), bb(t, x, device=torch.device("cuda"), k=29))
+
+
+def test_single_image_bank_known_answer():
+    """N=1: LS returns the bank image itself (mu = T_0), ELS mu lies in the convex hull of its pixels."""
+    bank = (torch.rand(1, 3, 16, 16, generator=torch.Generator().manual_seed(0)) * 255).round() / 127.5 - 1
+    labels = torch.zeros(1, dtype=torch.long)
+    x = torch.randn(1, 3, 16, 16, generator=torch.Generator().manual_seed(1)).cuda()
+    t, beta = torch.tensor([0.5]), None
+    from oracle import score_oracle as so
+    beta = float(so.cosine_beta(0.5))
+    ls = _make("LS", (bank, labels), 3, 1, None)
+    mu = _mu_from_score(ls(t, x, device=torch.device("cuda")).cpu().double(), x.cpu().double(), beta)
+    assert torch.allclose(mu, bank.double(), atol=1e-5)
+    els = _make("ELS", (bank, labels), 3, 1, None)
+    mu = _mu_from_score(els(t, x, device=torch.device("cuda")).cpu().double(), x.cpu().double(), beta)
+    assert float(mu.max()) <= float(bank.max()) + 1e-4 and float(mu.min()) >= float(bank.min()) - 1e-4
+
+
+def test_input_not_mutated_and_errors():
+    bank = torch.zeros(4, 3, 16, 16)
+    labels = torch.zeros(4, dtype=torch.long)
+    mod = _make("ELS", (bank, labels), 3, 4, None)
+    x = torch.randn(1, 3, 16, 16).cuda()
+    x0 = x.clone()
+    mod(torch.tensor([0.5]), x, device=torch.device("cuda"))
+    assert torch.equal(x, x0)
+    with pytest.raises(RuntimeError):
+        mod(torch.tensor([0.5]), x, device=torch.device("cpu"))
+    with pytest.raises(ValueError):
+        mod(torch.tensor([0.5]), x, device=torch.device("cuda"), k=4)

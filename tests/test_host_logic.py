@@ -1,0 +1,116 @@
+"""CPU tests: host-side selection logic against the oracle's replay of the DataLoader loop, the C-ABI
+library's exported symbols, the DDIM coefficient table."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import score_oracle as so
+from convolutional_diffusion_b200 import selection as sel
+from convolutional_diffusion_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("kind", ["LS", "ELS", "bbELS"])
+@pytest.mark.parametrize("n,bs,label,ms", [
+    (40, 16, None, None), (40, 16, 3, None), (48, 12, 1, 30), (48, 12, None, 30), (100, 7, 2, 50),
+    (100, 100, None, None), (33, 8, 0, 8), (64, 16, 9, None), (64, 16, None, 0), (10, 64, 1, 5),
+])
+def test_select_matches_oracle(kind, n, bs, label, ms):
+    rng = np.random.default_rng(n * 31 + bs)
+    labels = rng.integers(0, 4, n)
+    for order in (None, rng.permutation(n)):
+        i0, w0 = so.select_bank(kind, labels, label, bs, ms, order)
+        i1, w1 = sel.select(kind, labels, label, bs, ms, order)
+        assert np.array_equal(i0, i1)
+        assert np.allclose(w0, w1)
+
+
+def test_shard_partition():
+    idx = np.arange(103)
+    logw = -np.log(np.arange(1, 104, dtype=np.float64))
+    seen = []
+    for r in range(8):
+        i, w = sel.shard(idx, logw, r, 8)
+        assert np.allclose(w, logw[i])
+        seen.append(i)
+    assert np.array_equal(np.sort(np.concatenate(seen)), idx)
+    assert max(len(s) for s in seen) - min(len(s) for s in seen) <= 1
+
+
+def test_shuffle_order_matches_dataloader():
+    """LS hard-codes shuffle=True (idealscore.py:489): reproduce the DataLoader's permutation for a given
+    global RNG state."""
+    from torch.utils.data import DataLoader, TensorDataset
+    ds = TensorDataset(torch.arange(50))
+    torch.manual_seed(123)
+    got = [int(v) for (b,) in DataLoader(ds, batch_size=7, shuffle=True) for v in b]
+    torch.manual_seed(123)
+    mine = sel.dataloader_shuffle_order(50)
+    assert got == [int(v) for v in mine]
+
+
+def test_ddim_coefficients_match_oracle():
+    from convolutional_diffusion_b200.machine import ddim_coefficients
+    for nsteps in (6, 20):
+        mine = ddim_coefficients(nsteps)
+        ref = so.machine_coeffs(nsteps)
+        assert len(mine) == nsteps - 1
+        for (i, bt, cx, cmu), (j, bt2, bp2, cx_eps, ce) in zip(mine, ref):
+            assert i == j and abs(bt - bt2) < 1e-6
+            # x' = cx_eps x + ce eps with eps = (x - a mu)/sqrt(bt)  ==>  coefficients of x and mu
+            a = math.sqrt(1 - bt2)
+            assert abs(cx - (cx_eps + ce / math.sqrt(bt2))) < 1e-5
+            assert abs(cmu - (-ce * a / math.sqrt(bt2))) < 1e-5
+
+
+def test_schedules_match_golden():
+    from conftest import load_case, GOLDEN
+    from convolutional_diffusion_b200 import cosine_noise_schedule, exponential_schedule
+    c = load_case(os.path.join(GOLDEN, "schedule.npz"))
+    t = torch.from_numpy(c["t"])
+    assert np.allclose(cosine_noise_schedule(t).numpy(), c["cosine"], atol=1e-7)
+    assert np.allclose(exponential_schedule(t).numpy(), c["exponential"], atol=1e-7)
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports exactly what include/cdscore.h declares."""
+    from convolutional_diffusion_b200 import build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "cdscore.h")).read()
+    declared = set(re.findall(r"\b(cds_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.cds_abi_version() == 1
+    # geometry query is host-only arithmetic: CIFAR shape, k=17, two query passes fits in 227 KB
+    assert 0 < loaded.cds_els_umma_smem_bytes(3, 32, 32, 17, 2, 1) <= 227 * 1024
+    assert loaded.cds_els_umma_smem_bytes(3, 64, 64, 17, 2, 1) == 0      # not yet: falls back to the SIMT kernel
+    assert loaded.cds_els_umma_smem_bytes(3, 32, 32, 4, 1, 1) == 0       # even kernel sizes are rejected
+
+
+def test_no_cpu_fallback():
+    """Without CUDA the product path must fail loudly, not fall back."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from convolutional_diffusion_b200 import LocalEquivScoreModule
+    mod = LocalEquivScoreModule((torch.zeros(4, 3, 8, 8), torch.zeros(4, dtype=torch.long)), kernel_size=3)
+    with pytest.raises(RuntimeError):
+        mod(torch.tensor([0.5]), torch.zeros(1, 3, 8, 8), device=torch.device("cpu"))
+    with pytest.raises(RuntimeError):
+        mod.engine("cuda")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "convolutional_diffusion_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
