@@ -46,6 +46,7 @@ struct UmmaGeom {
   int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
   int nvb;            // 8-column blocks of candidate patches
   int n_mma;          // table entries (per precision combination)
+  int zero_pair;      // 1: the last table entry pairs its K granule with the zero block of A
   int passes, bank_planes;
   int smem_A, smem_stage, smem_colinfo, smem_table, smem_bar, smem_total;
 };
@@ -280,7 +281,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               const uint32_t b_off =
                   (stage_addr + (uint32_t)pb * (g.img_bytes + g.tile_pad) + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
               for (int t = 0; t < g.n_mma; ++t) {
-                const uint2 e = sTable[t];
+                uint2 e = sTable[t];
+                // the zero block sits behind the last plane: seen from plane pa its distance shrinks by pa planes
+                if (pa && g.zero_pair && t == g.n_mma - 1) e.x -= ((uint32_t)(pa * g.a_plane) >> 4) << 16;
                 umma_bf16(d_tmem, a_hi | (uint64_t)(e.x + a_off), b_hi | (uint64_t)(e.y + b_off), idesc, accum);
                 accum = 1;
               }
@@ -460,6 +463,7 @@ int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom&
       }
       if (dx < k) { left[nleft].a = a0 + dx * 16; left[nleft].b = b0 + dx * 16; ++nleft; }
     }
+  g.zero_pair = nleft & 1;
   for (int q = 0; q < nleft; q += 2) {
     if (nm >= MAX_MMAS) return 0;
     if (q + 1 < nleft) {

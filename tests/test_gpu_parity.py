@@ -181,7 +181,7 @@ def test_full_bank_split_invariance(cifar_bank):
         eng.evaluate("ELS", x, beta, 5, sel, query_pad="circular", mu=mu, beta_min=0.3)
         outs.append(mu.clone())
         eng._splits = eng._splits_orig
-    assert torch.allclose(outs[0], outs[1], atol=1e-5)
+    assert torch.allclose(outs[0], outs[1], atol=3e-4)   # fp32 summation order + ex2.approx; tolerance is 1e-3
 
 
 def test_full_bank_ls_equals_bbels_when_k_ge_h():
