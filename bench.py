@@ -282,7 +282,7 @@ def run_ours(args, scales):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 operands (hi+lo query split), f32 accumulate/softmax" if args.precision != "bf16" else "bf16",
+            "dtype": "f16 operands (hi+lo query split where a/beta > 1), f32 accumulate/softmax" if args.precision != "f16" else "f16",
             "data": "synthetic",
             "config": {"workload": "els_cifar10_conditional", "bank": N_BANK, "image": [C, H, W], "scales": SCALES_NAME,
                        "evals_per_trajectory": len(scales) - 1, "batch": B, "precision": args.precision,
@@ -309,7 +309,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "bf16x2"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16", "f16x2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -5,13 +5,13 @@ The reference re-reads and re-transforms the whole dataset through a DataLoader 
 (:441).  Here the images are uploaded once and kept in two layouts:
 
   images  fp32 planar [N,C,H,W]            exact values; SIMT kernels, patch norms, LS stream
-  strip8  bf16 [N,C,H,W,8] (+ residual)    tensor-core stream: one 16-byte granule = 8 vertically adjacent
+  strip8  fp16 [N,C,H,W,8] (+ residual)    tensor-core stream: one 16-byte granule = 8 vertically adjacent
                                            pixels, so overlapping k x k patches alias the same bytes
                                            (implicit im2col, see csrc/els_umma.cu)
 
 8-bit image datasets normalised with mean 0.5 / std 0.5 (`src/utils/data.py:63-70`) are odd integers / 255,
-which bf16 represents exactly after scaling by 255 -> a single bf16 plane carries the bank losslessly.
-Other banks get a second residual plane.
+which fp16 represents exactly after scaling by 255 -> a single fp16 plane carries the bank losslessly.
+Other banks are scaled by 256 and get a second plane holding the fp16 rounding residual.
 """
 from __future__ import annotations
 
@@ -67,20 +67,20 @@ class PatchBank:
 
     # ---- layouts -------------------------------------------------------------------------------
     def strip8(self):
-        """(hi, lo or None, scale): the bf16 strip layout for the tensor-core kernel."""
+        """(hi, lo or None, scale): the fp16 strip layout for the tensor-core kernel."""
         if self._strip is None:
             with torch.cuda.device(self.device):
                 v = self.images * 127.5 + 127.5                    # back to the 0..255 grid of ToTensor()
                 exact8 = bool(((v - v.round()).abs().max() < 1e-3).item()) and bool((v.min() > -0.5).item()) \
                     and bool((v.max() < 255.5).item())
-                scale = 255.0 if exact8 else 1.0
+                scale = 255.0 if exact8 else 256.0
                 n = self.N * self.C * self.H * self.W
-                hi = torch.empty(n * 8, dtype=torch.bfloat16, device=self.device)
+                hi = torch.empty(n * 8, dtype=torch.float16, device=self.device)
                 _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
                                                     scale, 0, _lib.ptr(hi), _lib.stream_ptr()), "cds_pack_strip8")
                 lo = None
                 if not exact8:
-                    lo = torch.empty(n * 8, dtype=torch.bfloat16, device=self.device)
+                    lo = torch.empty(n * 8, dtype=torch.float16, device=self.device)
                     _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
                                                         scale, 1, _lib.ptr(lo), _lib.stream_ptr()), "cds_pack_strip8")
                 self._strip = (hi, lo, scale)

@@ -8,7 +8,7 @@
 //
 // How (B200-first, not a translation of unfold+conv2d):
 //   * The bank lives in HBM as "strip8": one 16-byte granule = 8 vertically adjacent pixels
-//     [n][c][u][x][8] bf16.  With K-major, no-swizzle UMMA descriptors the row pitch inside an 8-row core
+//     [n][c][u][x][8] fp16.  With K-major, no-swizzle UMMA descriptors the row pitch inside an 8-row core
 //     matrix is 16 bytes, so 8 consecutive B rows = 8 horizontally adjacent patches, the next K granule
 //     (LBO = 16 B) = the next patch column dx, and the 8-row-group stride (SBO = one image row of granules)
 //     = the next patch row u.  Overlapping patches therefore alias the SAME shared-memory bytes: patches are
@@ -114,12 +114,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -132,7 +131,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the wait names the destination registers as in/out operands so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+// packed fp32x2 arithmetic (sm_100+): two FMAs per issue slot
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -204,7 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     const float* xb = p.x + (size_t)b * C * g.H * g.W;
     for (int e = tid; e < per_plane; e += THREADS) {
       const int jj = e % JW, gi = (e / JW) % TI, blk = (e / (JW * TI)) % g.nb, c = e / (JW * TI * g.nb);
-      __nv_bfloat16 hi[8], lo[8];
+      __half hi[8], lo[8];
       int xc = j0 + jj - g.d;
       bool colok = true;
       if (p.pad == CDS_PAD_CIRCULAR) xc = ((xc % g.W) + g.W) % g.W;
@@ -217,8 +250,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         if (p.pad == CDS_PAD_CIRCULAR) yr = ((yr % g.H) + g.H) % g.H;
         else ok = ok && (yr >= 0 && yr < g.H);
         const float v = ok ? xb[(c * g.H + yr) * g.W + xc] : 0.f;
-        hi[q] = __float2bfloat16_rn(v);
-        lo[q] = __float2bfloat16_rn(v - __bfloat162float(hi[q]));
+        hi[q] = __float2half_rn(v);
+        lo[q] = __float2half_rn(v - __half2float(hi[q]));
       }
       const size_t off = (size_t)(c * g.nb + blk) * g.a_block + (size_t)gi * g.RA + (size_t)jj * 16;
       *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<uint4*>(hi);
@@ -263,9 +296,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
         for (int ch = 0; ch < g.nchunks; ++ch) {
           const uint32_t N = 8u * g.chunk_g[ch];
-          // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+          // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
           // N>>3 at [17,23), M>>4 at [24,29)
-          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+          const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
           for (int vb = 0; vb < g.nvb; ++vb, ++T) {
             const int buf = (int)(T & 1);
             mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((T >> 1) & 1) ^ 1), 3);
@@ -280,11 +313,18 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               const uint32_t a_off = a_base + ((uint32_t)(pa * g.a_plane) >> 4);
               const uint32_t b_off =
                   (stage_addr + (uint32_t)pb * (g.img_bytes + g.tile_pad) + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
-              for (int t = 0; t < g.n_mma; ++t) {
-                uint2 e = sTable[t];
-                // the zero block sits behind the last plane: seen from plane pa its distance shrinks by pa planes
-                if (pa && g.zero_pair && t == g.n_mma - 1) e.x -= ((uint32_t)(pa * g.a_plane) >> 4) << 16;
-                umma_bf16(d_tmem, a_hi | (uint64_t)(e.x + a_off), b_hi | (uint64_t)(e.y + b_off), idesc, accum);
+              // the zero block sits behind the last plane: seen from plane pa its distance shrinks by pa planes
+              const uint32_t zfix = (pa && g.zero_pair) ? (((uint32_t)(pa * g.a_plane) >> 4) << 16) : 0u;
+              const int nm = g.n_mma;
+#pragma unroll 4
+              for (int t = 0; t < nm - 1; ++t) {
+                const uint2 e = sTable[t];
+                umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_off), b_hi | (uint64_t)(e.y + b_off), idesc, accum);
+                accum = 1;
+              }
+              {
+                const uint2 e = sTable[nm - 1];
+                umma_f16(d_tmem, a_hi | (uint64_t)(e.x - zfix + a_off), b_hi | (uint64_t)(e.y + b_off), idesc, accum);
                 accum = 1;
               }
             }
@@ -299,15 +339,68 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     const int wg = (warp - 4) >> 2, q = tid - 128 - wg * 128;   // q = query row = TMEM lane
     const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-    float4* col = sCol + wg * 256;
+    // per-warpgroup column info (4 KB): bias[256] | {v0,v1} of column pairs as float4[128] | v2 pairs float2[128]
+    float* colB = reinterpret_cast<float*>(sCol) + wg * 1024;
+    float* colV01 = colB + 256;
+    float* colV2 = colB + 768;
     const float c1 = CDS_LOG2E * a / beta * p.inv_scale;
     const float cpn = -CDS_LOG2E * a * a / (2.f * beta);
-    float m = -INFINITY, l = 0.f, acc[C];
+    const float2 c1c1 = make_float2(c1, c1);
+    // softmax state; even / odd columns accumulate separately (packed math, shorter dependency chains)
+    float m = -INFINITY;
+    float2 l2 = make_float2(0.f, 0.f), acc2[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int c = 0; c < C; ++c) acc2[c] = make_float2(0.f, 0.f);
     float* dbg = (p.dbg && split == 0 && qi < g.H && qj < g.W)
                      ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
                      : nullptr;
+    int u0 = 0, vb = 0;
+    bool dump = false;
+
+    auto process = [&](uint32_t* r, int c0) {
+      float2 t[8];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 bb = *reinterpret_cast<const float4*>(colB + c0 + 4 * e);
+        t[2 * e] = fma2(make_float2(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1])), c1c1, make_float2(bb.x, bb.y));
+        t[2 * e + 1] = fma2(make_float2(__uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])), c1c1, make_float2(bb.z, bb.w));
+        cmax = max3(cmax, t[2 * e].x, t[2 * e].y);
+        cmax = max3(cmax, t[2 * e + 1].x, t[2 * e + 1].y);
+      }
+      if (dump) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int u = u0 + ((c0 + e) >> 3), v = 8 * vb + ((c0 + e) & 7);
+          if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[e]) * p.inv_scale;
+        }
+      }
+      if (cmax > m) {                        // rare after the first few images
+        const float sc = ex2(m - cmax);
+        const float2 sc2 = make_float2(sc, sc);
+        l2 = mul2(l2, sc2);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc2[c] = mul2(acc2[c], sc2);
+        m = cmax;
+      }
+      const float2 nm2 = make_float2(-m, -m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 ar = add2(t[e], nm2);
+        const float2 w = make_float2(ex2(ar.x), ex2(ar.y));
+        l2 = add2(l2, w);
+        const int pr = (c0 >> 1) + e;
+        if (C == 1) {
+          acc2[0] = fma2(w, *reinterpret_cast<const float2*>(colV01 + 4 * pr), acc2[0]);
+        } else {
+          const float4 v01 = *reinterpret_cast<const float4*>(colV01 + 4 * pr);
+          acc2[0] = fma2(w, make_float2(v01.x, v01.y), acc2[0]);
+          acc2[1 % C] = fma2(w, make_float2(v01.z, v01.w), acc2[1 % C]);
+          if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(colV2 + 2 * pr), acc2[2 % C]);
+        }
+      }
+    };
+
     long long T = 0;
     for (int n = 0; n < n_img; ++n) {
       const int s = n % NUM_STAGES;
@@ -315,66 +408,51 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
       const float* pn = reinterpret_cast<const float*>(st + g.pn_off);
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
+      dump = (dbg != nullptr) && n == 0;
       for (int ch = 0; ch < g.nchunks; ++ch) {
-        const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
-        for (int vb = 0; vb < g.nvb; ++vb, ++T) {
+        const int N = 8 * g.chunk_g[ch];
+        u0 = g.chunk_u0[ch];
+        for (vb = 0; vb < g.nvb; ++vb, ++T) {
           if ((int)(T & 1) != wg) continue;
           const int buf = wg;
           // per-column bias and centre pixel of this tile's candidates: column r = 8*gr + rr <-> (u0+gr, 8*vb+rr)
-          bar_sync_named(1 + wg, 128);   // everyone done reading col[] of the previous tile
+          bar_sync_named(1 + wg, 128);   // everyone done reading the column info of the previous tile
           for (int r = q; r < N; r += 128) {
             const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
             const bool valid = (u < g.Ph) && (v < g.Pw);
-            float4 ci;
-            ci.x = valid ? fmaf(pn[valid ? u * g.Pw + v : 0], cpn, lw) : -INFINITY;
+            colB[r] = valid ? fmaf(pn[valid ? u * g.Pw + v : 0], cpn, lw) : -INFINITY;
             float vals[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < C; ++c) {
               const size_t go = ((size_t)(c * g.H + u + g.d) * g.W + (v + g.d)) * 16;
-              float t = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(st + go));
+              float t = __half2float(*reinterpret_cast<const __half*>(st + go));
               if (g.bank_planes > 1)
-                t += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(st + g.img_bytes + g.tile_pad + go));
+                t += __half2float(*reinterpret_cast<const __half*>(st + g.img_bytes + g.tile_pad + go));
               vals[c] = valid ? t * p.inv_scale : 0.f;
             }
-            ci.y = vals[0]; ci.z = vals[1]; ci.w = vals[2];
-            col[r] = ci;
+            const int pr = r >> 1, hf = r & 1;
+            colV01[4 * pr + hf] = vals[0];
+            colV01[4 * pr + 2 + hf] = vals[1];
+            colV2[2 * pr + hf] = vals[2];
           }
           bar_sync_named(1 + wg, 128);
           mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
           tc_fence_after();
           const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
-          for (int c0 = 0; c0 < N; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
-            float t[16], cmax = -INFINITY;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              t[e] = fmaf(__uint_as_float(r[e]), c1, col[c0 + e].x);
-              cmax = fmaxf(cmax, t[e]);
-            }
-            if (dbg && n == 0) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int u = u0 + ((c0 + e) >> 3), v = 8 * vb + ((c0 + e) & 7);
-                if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[e]) * p.inv_scale;
-              }
-            }
-            const float m_new = fmaxf(m, cmax);
-            const float sc = ex2(m - m_new);
-            l *= sc;
-#pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] *= sc;
-            m = m_new;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float4 ci = col[c0 + e];
-              const float w = ex2(t[e] - m);
-              l += w;
-              acc[0] = fmaf(w, ci.y, acc[0]);
-              if (C > 1) acc[1 % C] = fmaf(w, ci.z, acc[1 % C]);
-              if (C > 2) acc[2 % C] = fmaf(w, ci.w, acc[2 % C]);
-            }
+          // software pipelined TMEM reads: the next 16 columns are in flight while these are consumed
+          uint32_t r0[16], r1[16];
+          tmem_ld16(taddr, r0);
+          for (int c0 = 0;;) {
+            tmem_ld_wait16(r0);
+            if (c0 + 16 < N) tmem_ld16(taddr + c0 + 16, r1);
+            process(r0, c0);
+            c0 += 16;
+            if (c0 >= N) break;
+            tmem_ld_wait16(r1);
+            if (c0 + 16 < N) tmem_ld16(taddr + c0 + 16, r0);
+            process(r1, c0);
+            c0 += 16;
+            if (c0 >= N) break;
           }
           tc_fence_before();
           __syncwarp();
@@ -384,6 +462,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     }
+    float l = l2.x + l2.y, acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = acc2[c].x + acc2[c].y;
     // merge the two warpgroups' partial softmax states and write this split's partials
     if (wg == 1) {
       sMerge[q * (2 + C) + 0] = m;

@@ -127,12 +127,12 @@ __global__ void pack_strip8_kernel(const float* __restrict__ images, long long N
     const int u = (g / W) % H;
     const long long nc = g / ((long long)W * H);
     const float* src = images + nc * H * W;
-    __nv_bfloat16 h[8];
+    __half h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = (u + e < H) ? src[(u + e) * W + xx] * scale : 0.f;
-      __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      h[e] = plane == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+      __half hi = __float2half_rn(v);
+      h[e] = plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
     }
     out[g] = *reinterpret_cast<uint4*>(h);
   }
@@ -242,12 +242,12 @@ extern "C" int cds_partials_simt(int kind, int query_pad, const float* x, int B,
 }
 
 extern "C" int cds_pack_strip8(const float* images, int64_t N, int C, int H, int W, float scale, int plane,
-                               void* out_bf16, void* stream) {
+                               void* out_f16, void* stream) {
   CDS_CHECK_ARG(N >= 1 && C >= 1 && H >= 1 && W >= 1, "cds_pack_strip8: empty bank");
   const long long total = (long long)N * C * H * W;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads > 148 * 32 ? 148 * 32 : (total + threads - 1) / threads);
-  pack_strip8_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(images, N, C, H, W, scale, plane, (uint4*)out_bf16);
+  pack_strip8_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(images, N, C, H, W, scale, plane, (uint4*)out_f16);
   CDS_CHECK_LAUNCH("pack_strip8_kernel");
   return CDS_OK;
 }

@@ -38,7 +38,7 @@ class Partials:
 class ScoreEngine:
     """Evaluates one score module kind against a PatchBank."""
 
-    def __init__(self, bank: PatchBank, precision="bf16x2", use_tensor_cores=True, group=None):
+    def __init__(self, bank: PatchBank, precision="f16x2", use_tensor_cores=True, group=None):
         self.bank = bank
         self.lib = bank.lib
         self.device = bank.device
@@ -56,14 +56,16 @@ class ScoreEngine:
         return self._buf[key]
 
     def passes_for(self, k, beta_min):
-        if self.precision == "bf16":
+        """Tensor-core passes over the query: 1 = fp16 query (11-bit significand), 2 = fp16 hi + lo residual
+        (22 bits, fp32-grade).  "auto" uses one pass while the logit gain a/beta that multiplies the dot-product
+        rounding error is <= 1: measured on the headline workload (profiles/r01_precision_probe.log) the
+        denoised estimate then moves by < 2e-4 max-abs, 5x inside the 1e-3 tolerance."""
+        if self.precision == "f16":
             return 1
-        if self.precision == "bf16x2":
+        if self.precision == "f16x2":
             return 2
-        # "auto": one bf16 pass when the logit error it causes stays below ~1e-2
-        d = k * k * self.bank.C
         a_over_b = (max(1.0 - beta_min, 0.0) ** 0.5) / max(beta_min, 1e-6)
-        return 1 if a_over_b * (d ** 0.5) * 2.0 ** -9 < 1e-2 else 2
+        return 1 if a_over_b <= 1.0 else 2
 
     def umma_supported(self, k, passes):
         b = self.bank

@@ -50,7 +50,7 @@ class _ScoreModuleBase(nn.Module):
     query_pad = None
 
     def __init__(self, dataset, kernel_size, batch_size, image_size, schedule, max_samples, shuffle,
-                 precision="bf16x2", use_tensor_cores=True, process_group=None, bank=None):
+                 precision="f16x2", use_tensor_cores=True, process_group=None, bank=None):
         super().__init__()
         self.dataset = dataset
         self.batch_size = batch_size

@@ -40,12 +40,12 @@ int         cds_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* ---- bank preparation (once per bank; replaces the per-call DataLoader pass, idealscore.py:184,430,521) */
 
 /* Pack planar fp32 images into the tensor-core streaming layout "strip8":
- *   out[n][c][u][x][8] (bf16), element e = scale * img[n][c][u+e][x]  (0 beyond the last row).
+ *   out[n][c][u][x][8] (fp16), element e = scale * img[n][c][u+e][x]  (0 beyond the last row).
  * One 16-byte granule = an 8-pixel vertical strip, so a k x k patch row block is addressable with
  * 16-byte-stride UMMA descriptors (implicit im2col; patches are never materialised).
- * plane = 0: bf16(scale*v);  plane = 1: bf16 of the rounding residual (second plane for non-8-bit banks). */
+ * plane = 0: fp16(scale*v);  plane = 1: fp16 of the rounding residual (second plane for non-8-bit banks). */
 int cds_pack_strip8(const float* images, int64_t N, int C, int H, int W, float scale, int plane,
-                    void* out_bf16, void* stream);
+                    void* out_f16, void* stream);
 
 /* ||p||^2 of every valid (un-padded) k x k x C patch: out[n][H-k+1][W-k+1]  (idealscore.py:451,243) */
 int cds_patch_norms(const float* images, int64_t N, int C, int H, int W, int k, float* out, void* stream);
@@ -63,7 +63,7 @@ int cds_partials_simt(int kind, int query_pad, const float* x, int B, int C, int
 
 /* tcgen05 / TMEM evaluation of ELS (and the bbELS centre region): queries = all H*W pixels of x padded
  * per query_pad, candidates = every valid k x k patch of the selected images, streamed from the strip8
- * bank by bulk-async copies.  passes = 1: bf16 query; 2: bf16 hi+lo query (fp32-grade dot products for
+ * bank by bulk-async copies.  passes = 1: fp16 query; 2: fp16 hi+lo query (fp32-grade dot products for
  * 8-bit banks).  bank_lo may be NULL (8-bit-exact bank).  dbg_dots: optional [B][H*W][P] raw dot dump of the
  * first selected image (tests only, may be NULL). */
 int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k,

@@ -29,7 +29,7 @@ def main():
     for (C, H, k, passes, pad) in cases:
         imgs, labels = synthetic_bank(6, C, H, seed=1)
         bank = PatchBank(imgs, labels, device="cuda")
-        eng = ScoreEngine(bank, precision="bf16x2" if passes == 2 else "bf16")
+        eng = ScoreEngine(bank, precision="f16x2" if passes == 2 else "f16")
         ok = eng.umma_supported(k, passes)
         print(f"C={C} H={H} k={k} passes={passes} pad={pad} supported={ok}", flush=True)
         if not ok:

@@ -17,7 +17,7 @@ def main():
     bank, labels = synthetic_bank(50000, 3, 32, seed=0)
     scales = load_scales("CIFAR10_ResNet_zeros_conditional")
     mod = LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=64, schedule=cosine_noise_schedule,
-                                precision="bf16x2")
+                                precision="f16x2")
     machine = ScheduledScoreMachine(mod, in_channels=3, imsize=32, scales=scales)
     eng = mod.engine("cuda")
     for label in (0, 5):

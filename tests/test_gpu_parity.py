@@ -222,3 +222,34 @@ def test_input_not_mutated_and_errors():
         mod(torch.tensor([0.5]), x, device=torch.device("cpu"))
     with pytest.raises(ValueError):
         mod(torch.tensor([0.5]), x, device=torch.device("cuda"), k=4)
+
+
+@pytest.mark.parametrize("precision", ["auto", "f16x2"])
+def test_cifar_schedule_every_step(precision):
+    """The headline schedule (scales_CIFAR10_ResNet_zeros_conditional, 19 evaluations, class conditional) on a
+    bank small enough for the float64 oracle: mu max-abs <= 1e-3 at EVERY step, final sample PSNR >= 50 dB."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.scales import load_scales
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    cd = _mods()
+    scales = load_scales("CIFAR10_ResNet_zeros_conditional")
+    bank, labels = synthetic_bank(60, 3, 32, nlabels=3, seed=21)
+    label, bs = 1, 64
+    mod = _make("ELS", (bank, labels), 3, bs, None, precision=precision)
+    machine = cd.ScheduledScoreMachine(mod, in_channels=3, imsize=32, scales=scales)
+    x = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(77))
+    out, rec = machine.trajectory(x.cuda(), label=torch.tensor([label]), device="cuda")
+    idx, logw = so.select_bank("ELS", labels.numpy(), label, bs, None)
+    sub = bank.numpy()[idx]
+    assert len(rec) == 19
+    worst = 0.0
+    for r in rec:
+        mu_o = so.els_mu(r["x"][0].cpu().numpy(), sub, r["beta"], r["k"], logw)
+        err = float(np.max(np.abs(r["mu"][0].cpu().double().numpy() - mu_o)))
+        worst = max(worst, err)
+        assert err < MU_TOL, (r["i"], r["k"], err)
+    ref = so.run_machine("ELS", x[0].numpy(), sub, scales, logw)
+    got = out[0].cpu().double().numpy()
+    psnr = 10 * np.log10(4.0 / max(float(np.mean((got - ref) ** 2)), 1e-30))
+    assert psnr >= 50.0, psnr
+    print(f"precision={precision}: worst per-step mu error {worst:.2e}, final PSNR {psnr:.1f} dB")
