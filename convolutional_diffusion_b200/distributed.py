@@ -22,9 +22,9 @@ def gather_partials(m, l, acc, group=None):
     out = []
     for t in (m, l, acc):
         t = t.contiguous()
-        g = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(g, t, group=group)
-        out.append(g)
+        g = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(g, t, group=group)          # rank-major concatenation along dim 0
+        out.append(g.view((world,) + tuple(t.shape)))
     return out
 
 
