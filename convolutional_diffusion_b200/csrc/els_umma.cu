@@ -26,7 +26,8 @@ namespace {
 constexpr int TI = 16, TJ = 8;           // query tile: 16 rows x 8 columns = 128 queries = UMMA M
 constexpr int NUM_STAGES = 2;
 constexpr int MAX_CHUNKS = 4;
-constexpr int THREADS = 128 + 256;       // 4 control warps + 2 epilogue warpgroups
+constexpr int NUM_EPI_WG = 4;            // epilogue warpgroups: a pair per TMEM buffer, splitting its columns
+constexpr int THREADS = 128 + 128 * NUM_EPI_WG;   // 4 control warps + the epilogue warpgroups
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_MMAS = 192;
 
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 8 * NUM_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * NUM_STAGES, bar_tempty = bar_tfull + 16;
   uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sBar + 2 * NUM_STAGES + 4);
-  float* sMerge = reinterpret_cast<float*>(sBar + 2 * NUM_STAGES + 6);               // [128][2+C]
+  float* sMerge = reinterpret_cast<float*>(sCol);   // [NUM_EPI_WG-1][128][2+C], aliases the column tables once all tiles are done
 
   const float beta = p.beta[b];
   const float a = sqrtf(1.f - beta);
@@ -213,11 +214,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   if (tid == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1 + 8);   // MMA commit + 8 epilogue warps
+      mbar_init(bar_empty + 8 * s, 1 + 4 * NUM_EPI_WG);   // MMA commit + every epilogue warp
     }
     for (int q = 0; q < 2; ++q) {
       mbar_init(bar_tfull + 8 * q, 1);
-      mbar_init(bar_tempty + 8 * q, 4);
+      mbar_init(bar_tempty + 8 * q, 2 * NUM_EPI_WG);   // the warps of the two warpgroups sharing this buffer
     }
     fence_barrier_init();
   }
@@ -336,11 +337,13 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     }
   } else if (warp >= 4) {
     // =========================== epilogue: two warpgroups, tile T handled by warpgroup T&1 from TMEM buffer T&1
+    // warpgroup wg: TMEM buffer / tile parity pr = wg & 1, column half hf = wg >> 1 (chunks hf, hf+2, ... of 16 columns)
     const int wg = (warp - 4) >> 2, q = tid - 128 - wg * 128;   // q = query row = TMEM lane
+    const int pr2 = wg & 1, hf2 = wg >> 1, q2 = q + 128 * hf2;   // q2: index inside the 256-thread pair
     const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     // per-warpgroup column info (4 KB): bias[256] | {v0,v1} of column pairs as float4[128] | v2 pairs float2[128]
-    float* colB = reinterpret_cast<float*>(sCol) + wg * 1024;
+    float* colB = reinterpret_cast<float*>(sCol) + pr2 * 1024;
     float* colV01 = colB + 256;
     float* colV2 = colB + 768;
     const float c1 = CDS_LOG2E * a / beta * p.inv_scale;
@@ -375,6 +378,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[e]) * p.inv_scale;
         }
       }
+      // every weight of this chunk is < 2^-40 of the running sum's scale for all 32 queries of the warp: adding
+      // them cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
+      if (__all_sync(0xffffffffu, cmax < m - 40.f)) return;
       if (cmax > m) {                        // rare after the first few images
         const float sc = ex2(m - cmax);
         const float2 sc2 = make_float2(sc, sc);
@@ -413,11 +419,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         const int N = 8 * g.chunk_g[ch];
         u0 = g.chunk_u0[ch];
         for (vb = 0; vb < g.nvb; ++vb, ++T) {
-          if ((int)(T & 1) != wg) continue;
-          const int buf = wg;
+          if ((int)(T & 1) != pr2) continue;
+          const int buf = pr2;
           // per-column bias and centre pixel of this tile's candidates: column r = 8*gr + rr <-> (u0+gr, 8*vb+rr)
-          bar_sync_named(1 + wg, 128);   // everyone done reading the column info of the previous tile
-          for (int r = q; r < N; r += 128) {
+          bar_sync_named(1 + pr2, 256);   // everyone done reading the column info of the previous tile
+          for (int r = q2; r < N; r += 256) {
             const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
             const bool valid = (u < g.Ph) && (v < g.Pw);
             colB[r] = valid ? fmaf(pn[valid ? u * g.Pw + v : 0], cpn, lw) : -INFINITY;
@@ -435,24 +441,16 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             colV01[4 * pr + 2 + hf] = vals[1];
             colV2[2 * pr + hf] = vals[2];
           }
-          bar_sync_named(1 + wg, 128);
+          bar_sync_named(1 + pr2, 256);
           mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
           tc_fence_after();
           const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
-          // software pipelined TMEM reads: the next 16 columns are in flight while these are consumed
-          uint32_t r0[16], r1[16];
-          tmem_ld16(taddr, r0);
-          for (int c0 = 0;;) {
+          // this warpgroup's 16-column chunks: hf2, hf2 + 2, ...; the partner warpgroup takes the others
+          for (int c0 = 16 * hf2; c0 < N; c0 += 32) {
+            uint32_t r0[16];
+            tmem_ld16(taddr + c0, r0);
             tmem_ld_wait16(r0);
-            if (c0 + 16 < N) tmem_ld16(taddr + c0 + 16, r1);
             process(r0, c0);
-            c0 += 16;
-            if (c0 >= N) break;
-            tmem_ld_wait16(r1);
-            if (c0 + 16 < N) tmem_ld16(taddr + c0 + 16, r0);
-            process(r1, c0);
-            c0 += 16;
-            if (c0 >= N) break;
           }
           tc_fence_before();
           __syncwarp();
@@ -466,24 +464,37 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = acc2[c].x + acc2[c].y;
     // merge the two warpgroups' partial softmax states and write this split's partials
-    if (wg == 1) {
-      sMerge[q * (2 + C) + 0] = m;
-      sMerge[q * (2 + C) + 1] = l;
+    bar_sync_named(3, 128 * NUM_EPI_WG);       // column tables are dead from here on: reuse them for the merge
+    if (wg > 0) {
+      float* dst = sMerge + ((wg - 1) * 128 + q) * (2 + C);
+      dst[0] = m;
+      dst[1] = l;
 #pragma unroll
-      for (int c = 0; c < C; ++c) sMerge[q * (2 + C) + 2 + c] = acc[c];
+      for (int c = 0; c < C; ++c) dst[2 + c] = acc[c];
     }
-    bar_sync_named(3, 256);
+    bar_sync_named(3, 128 * NUM_EPI_WG);
     if (wg == 0 && qi < g.H && qj < g.W) {
-      const float m1 = sMerge[q * (2 + C) + 0], l1 = sMerge[q * (2 + C) + 1];
-      const float M = fmaxf(m, m1);
-      const float w0 = (m == -INFINITY) ? 0.f : ex2(m - M), w1 = (m1 == -INFINITY) ? 0.f : ex2(m1 - M);
+      float M = m;
+#pragma unroll
+      for (int w = 1; w < NUM_EPI_WG; ++w) M = fmaxf(M, sMerge[((w - 1) * 128 + q) * (2 + C)]);
+      float w0 = (m == -INFINITY) ? 0.f : ex2(m - M);
+      float L = l * w0, A[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) A[c] = acc[c] * w0;
+#pragma unroll
+      for (int w = 1; w < NUM_EPI_WG; ++w) {
+        const float* src = sMerge + ((w - 1) * 128 + q) * (2 + C);
+        const float ww = (src[0] == -INFINITY) ? 0.f : ex2(src[0] - M);
+        L = fmaf(src[1], ww, L);
+#pragma unroll
+        for (int c = 0; c < C; ++c) A[c] = fmaf(src[2 + c], ww, A[c]);
+      }
       const int HW = g.H * g.W, pix = qi * g.W + qj;
       const size_t o = ((size_t)split * p.B + b) * HW + pix;
       p.m[o] = M;
-      p.l[o] = l * w0 + l1 * w1;
+      p.l[o] = L;
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        p.acc[(((size_t)split * p.B + b) * C + c) * HW + pix] = acc[c] * w0 + sMerge[q * (2 + C) + 2 + c] * w1;
+      for (int c = 0; c < C; ++c) p.acc[(((size_t)split * p.B + b) * C + c) * HW + pix] = A[c];
     }
   }
   tc_fence_before();
@@ -562,7 +573,7 @@ int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom&
   g.smem_stage = NUM_STAGES * g.stage_bytes;
   g.smem_colinfo = 2 * 256 * 16;
   g.smem_table = (nm * 8 + 127) / 128 * 128;
-  g.smem_bar = 8 * (2 * NUM_STAGES + 4) + 16 + 128 * 5 * 4 + 64;
+  g.smem_bar = 8 * (2 * NUM_STAGES + 4) + 16 + 64;
   g.smem_total = g.smem_A + g.smem_stage + g.smem_colinfo + g.smem_table + g.smem_bar + 1024;
   if (g.smem_total > 227 * 1024) return 0;
   // the zero-block LBO (a_zero - a) must fit 14 bits of 16-byte units: a_bytes < 256 KB always holds here
