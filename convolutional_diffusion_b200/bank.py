@@ -63,6 +63,7 @@ class PatchBank:
         assert self.labels.shape[0] == self.N
         self._strip = None
         self._pnorm = {}
+        self._nplane = {}
         self._sel = {}
 
     # ---- layouts -------------------------------------------------------------------------------
@@ -95,6 +96,16 @@ class PatchBank:
                                                     _lib.ptr(out), _lib.stream_ptr()), "cds_patch_norms")
                 self._pnorm[k] = out
         return self._pnorm[k]
+
+    def norm_plane(self, k):
+        """fp16 [N,H,W,8] norm plane of kernel size k for the tensor-core kernel (computed once per k)."""
+        if k not in self._nplane:
+            with torch.cuda.device(self.device):
+                out = torch.empty(self.N * self.H * self.W * 8, dtype=torch.float16, device=self.device)
+                _lib.check(self.lib.cds_pack_norm_plane(_lib.ptr(self.images), self.N, self.C, self.H, self.W, k,
+                                                        _lib.ptr(out), _lib.stream_ptr()), "cds_pack_norm_plane")
+                self._nplane[k] = out
+        return self._nplane[k]
 
     # ---- selection -----------------------------------------------------------------------------
     def selection(self, kind, label, batch_size, max_samples, order=None, rank=0, world=1):

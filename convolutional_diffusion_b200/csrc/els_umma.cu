@@ -10,46 +10,59 @@
 //   * The bank lives in HBM as "strip8": one 16-byte granule = 8 vertically adjacent pixels
 //     [n][c][u][x][8] fp16.  With K-major, no-swizzle UMMA descriptors the row pitch inside an 8-row core
 //     matrix is 16 bytes, so 8 consecutive B rows = 8 horizontally adjacent patches, the next K granule
-//     (LBO = 16 B) = the next patch column dx, and the 8-row-group stride (SBO = one image row of granules)
-//     = the next patch row u.  Overlapping patches therefore alias the SAME shared-memory bytes: patches are
-//     never materialised, in HBM or in shared memory.  A whole image is staged by one cp.async.bulk.
+//     (LBO) = the next patch column dx, and the 8-row-group stride (SBO = one image row of granules) = the next
+//     patch row u.  Overlapping patches therefore alias the SAME shared-memory bytes: patches are never
+//     materialised, in HBM or in shared memory.  A whole image is staged by one cp.async.bulk.
 //   * The query side uses the same trick on a per-CTA tile of 16 x 8 pixels, with the K padding (dy >= k)
 //     zeroed on the query side only, so the bank can stay unmasked and k-independent.
+//   * The -a^2|p|^2/(2 beta) term rides in the SAME contraction: one extra K granule per patch holds |p|^2 as a
+//     three-way fp16 split (the per-k "norm plane", same strip addressing), its query-side partner holds the
+//     constant -a*scale/2, so the accumulator is already  scale*(q.p) - (a*scale/2)|p|^2  and the logit is a
+//     single multiply away.  Invalid patch positions carry a huge norm and vanish in the softmax.
 //   * One UMMA covers N = 8 * (#patch rows) <= 256 candidates x 128 queries x K = 16; accumulators ping-pong
-//     between two TMEM buffers; a producer warp, an MMA warp and two epilogue warpgroups run decoupled
-//     through mbarriers.  The epilogue is the flash-softmax: tcgen05.ld -> fma -> max -> ex2 -> weighted sum.
+//     between two TMEM buffers.  Warp roles: producer (bulk copies), MMA issuer (one thread), two builder warps
+//     (centre-pixel tables per image) and four epilogue warpgroups, decoupled through mbarriers.
+//   * Epilogue = flash softmax in two passes per 16-column chunk: (1) tcgen05.ld + 3-input max; a chunk whose
+//     best logit is 2^-40 below the running max for all 32 queries of the warp is skipped; (2) packed f32x2
+//     fma -> ex2 -> weighted sums.
 #include "common.cuh"
 #include "../../include/cdscore.h"
 
 namespace {
 
 constexpr int TI = 16, TJ = 8;           // query tile: 16 rows x 8 columns = 128 queries = UMMA M
-constexpr int NUM_STAGES = 2;
+constexpr int MAX_STAGES = 2;
 constexpr int MAX_CHUNKS = 4;
 constexpr int NUM_EPI_WG = 4;            // epilogue warpgroups: a pair per TMEM buffer, splitting its columns
 constexpr int THREADS = 128 + 128 * NUM_EPI_WG;   // 4 control warps + the epilogue warpgroups
 constexpr int TMEM_COLS = 512;
-constexpr int MAX_MMAS = 192;
+constexpr int MAX_MMAS = 320;
+constexpr float SKIP_LOG2 = 40.f;        // chunks whose weights are all < 2^-40 of the running max are skipped
+constexpr float INVALID_NORM = 60000.f;  // norm-plane marker of positions that are not valid patches
 
 struct UmmaGeom {
-  int C, H, W, k, d, Ph, Pw, Ppad;
+  int C, H, W, k, d, Ph, Pw;
   int nb;             // dy blocks of 8 rows
   int RA;             // bytes between query rows in the A tile = (k+7)*16
   int a_block;        // bytes of one (c,b) block of A = TI*RA
   int a_plane;        // bytes of one precision plane of A = C*nb*a_block
+  int a_const;        // byte offset of the constant (-a*scale/2) block in A
   int a_zero;         // byte offset of the zero block in A
-  int a_bytes;        // total A bytes (planes + zero block)
+  int a_bytes;
   int S1;             // bytes of one image row of granules = W*16
   int img_bytes;      // C*H*W*16
-  int tile_pad;       // zeroed guard after each B tile
-  int stage_bytes;    // bank_planes*(img_bytes+tile_pad) + Ppad*4, rounded to 128
-  int pn_off;         // offset of the norms inside a stage
+  int np_bytes;       // H*W*16 (norm plane of one image)
+  int tile_pad;       // zeroed guard after each staged tile
+  int np_off;         // offset of the norm plane inside a stage
+  int vt_off;         // offset of the centre-pixel table inside a stage
+  int vt_tile;        // floats per tile of that table: [N/2 pairs][4] (v0,v1) + [N/2][2] (v2)
+  int stage_bytes;
+  int stages;
   int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
   int nvb;            // 8-column blocks of candidate patches
-  int n_mma;          // table entries (per precision combination)
-  int zero_pair;      // 1: the last table entry pairs its K granule with the zero block of A
+  int n_mma;          // descriptor-table entries per accumulator tile (all precision combinations)
   int passes, bank_planes;
-  int smem_A, smem_stage, smem_colinfo, smem_table, smem_bar, smem_total;
+  int smem_A, smem_stage, smem_merge, smem_table, smem_bar, smem_total;
 };
 
 struct UmmaParams {
@@ -60,12 +73,12 @@ struct UmmaParams {
   const float* beta;
   const uint8_t* bank_hi;
   const uint8_t* bank_lo;
-  float inv_scale;
-  const float* pnorm;
+  const uint8_t* norm_plane;
+  float scale;
   const int32_t* idx;
   const float* logw;
   float *m, *l, *acc, *dbg;
-  uint2 table[MAX_MMAS];   // lo words of (A,B) descriptors relative to their bases
+  uint2 table[MAX_MMAS];   // lo words of the (A,B) descriptors relative to the A base / the tile origin in a stage
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -183,6 +196,7 @@ __device__ __forceinline__ uint64_t desc_hi(uint32_t sbo_bytes) {
   return ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 
+
 // ------------------------------------------------------------------ the kernel
 template <int C>
 __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_constant__ UmmaParams p) {
@@ -194,40 +208,42 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   const int split = blockIdx.y, b = blockIdx.z;
   const long long n0 = p.n_sel * split / p.splits, n1 = p.n_sel * (split + 1) / p.splits;
   const int n_img = (int)(n1 - n0);
-  const int tiles_per_img = g.nchunks * g.nvb;
+  const int S = g.stages;
 
   uint8_t* sA = smem;
   uint8_t* sStage = smem + g.smem_A;
-  float4* sCol = reinterpret_cast<float4*>(smem + g.smem_A + g.smem_stage);          // [2][256]
-  uint2* sTable = reinterpret_cast<uint2*>(smem + g.smem_A + g.smem_stage + g.smem_colinfo);
-  uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + g.smem_A + g.smem_stage + g.smem_colinfo + g.smem_table);
-  // barriers: full[S], empty[S], tfull[2], tempty[2]; then tmem base; then the WG1 -> WG0 merge scratch
-  const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 8 * NUM_STAGES;
-  const uint32_t bar_tfull = bar_empty + 8 * NUM_STAGES, bar_tempty = bar_tfull + 16;
-  uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sBar + 2 * NUM_STAGES + 4);
-  float* sMerge = reinterpret_cast<float*>(sCol);   // [NUM_EPI_WG-1][128][2+C], aliases the column tables once all tiles are done
+  float* sMerge = reinterpret_cast<float*>(smem + g.smem_A + g.smem_stage);           // [NUM_EPI_WG-1][128][2+C]
+  uint2* sTable = reinterpret_cast<uint2*>(smem + g.smem_A + g.smem_stage + g.smem_merge);
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + g.smem_A + g.smem_stage + g.smem_merge + g.smem_table);
+  // barriers: full[2], empty[2], vready[2], tfull[2], tempty[2]; then the TMEM base address
+  const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 16, bar_vready = bar_full + 32;
+  const uint32_t bar_tfull = bar_full + 48, bar_tempty = bar_full + 64;
+  uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sBar + 10);
 
   const float beta = p.beta[b];
   const float a = sqrtf(1.f - beta);
+  const float inv_scale = 1.f / p.scale;
 
   // ---- one-time setup: barriers, TMEM, descriptor table, zero guards, query tile (A operand)
   if (tid == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1 + 4 * NUM_EPI_WG);   // MMA commit + every epilogue warp
+      mbar_init(bar_vready + 8 * s, 2);                   // the two builder warps
     }
     for (int q = 0; q < 2; ++q) {
       mbar_init(bar_tfull + 8 * q, 1);
-      mbar_init(bar_tempty + 8 * q, 2 * NUM_EPI_WG);   // the warps of the two warpgroups sharing this buffer
+      mbar_init(bar_tempty + 8 * q, 2 * NUM_EPI_WG);      // the warps of the two warpgroups sharing this buffer
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
   for (int e = tid; e < g.n_mma; e += THREADS) sTable[e] = p.table[e];
-  // zero guards behind every staged image tile (over-reads of masked columns must stay finite)
-  for (int s = 0; s < NUM_STAGES; ++s)
-    for (int pl = 0; pl < g.bank_planes; ++pl) {
-      uint8_t* pad = sStage + (size_t)s * g.stage_bytes + (size_t)pl * (g.img_bytes + g.tile_pad) + g.img_bytes;
+  // zero guards behind every staged tile (over-reads of masked columns must stay finite)
+  for (int s = 0; s < S; ++s)
+    for (int pl = 0; pl <= g.bank_planes; ++pl) {
+      uint8_t* pad = sStage + (size_t)s * g.stage_bytes +
+                     (pl < g.bank_planes ? (size_t)pl * (g.img_bytes + g.tile_pad) + g.img_bytes : (size_t)g.np_off + g.np_bytes);
       for (int e = tid * 16; e < g.tile_pad; e += THREADS * 16) *reinterpret_cast<uint4*>(pad + e) = make_uint4(0, 0, 0, 0);
     }
   {
@@ -258,8 +274,18 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<uint4*>(hi);
       if (g.passes > 1) *reinterpret_cast<uint4*>(sA + g.a_plane + off) = *reinterpret_cast<uint4*>(lo);
     }
-    for (int e = tid * 16; e < g.a_block; e += THREADS * 16)
+    // constant block: every granule = three-way fp16 split of gamma = -a*scale/2, laid out against the norm plane's
+    // (ph, pm, pl, ph, pm, ph, 0, 0) so that the K sum is (gh+gm+gl)*(ph+pm+pl) up to terms below 2^-30
+    const float gamma = -0.5f * a * p.scale;
+    const __half gh = __float2half_rn(gamma);
+    const __half gm = __float2half_rn(gamma - __half2float(gh));
+    const __half gl = __float2half_rn(gamma - __half2float(gh) - __half2float(gm));
+    const __half z = __float2half_rn(0.f);
+    __half cg[8] = {gh, gh, gh, gm, gm, gl, z, z};
+    for (int e = tid * 16; e < g.a_block; e += THREADS * 16) {
+      *reinterpret_cast<uint4*>(sA + g.a_const + e) = *reinterpret_cast<uint4*>(cg);
       *reinterpret_cast<uint4*>(sA + g.a_zero + e) = make_uint4(0, 0, 0, 0);
+    }
   }
   fence_proxy_async();
   tc_fence_before();
@@ -268,20 +294,19 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   const uint32_t tmem_base = *sTmemBase;
 
   if (warp == 0) {
-    // =========================== producer: one bulk copy per image (+ its patch norms)
+    // =========================== producer: bulk copies of one image (+ residual plane) and its norm plane
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(g.bank_planes * g.img_bytes + g.Ppad * 4);
+      const uint32_t tx = (uint32_t)(g.bank_planes * g.img_bytes + g.np_bytes);
       for (int n = 0; n < n_img; ++n) {
-        const int s = n % NUM_STAGES;
-        const uint32_t ph = (n / NUM_STAGES) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
+        const int s = n % S;
+        mbar_wait(bar_empty + 8 * s, ((n / S) & 1) ^ 1, 1);
         const long long gi = p.idx[n0 + n];
         const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
         mbar_expect_tx(bar_full + 8 * s, tx);
         bulk_g2s(dst, p.bank_hi + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
         if (g.bank_planes > 1)
           bulk_g2s(dst + g.img_bytes + g.tile_pad, p.bank_lo + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
-        bulk_g2s(dst + g.pn_off, p.pnorm + (size_t)gi * g.Ppad, g.Ppad * 4, bar_full + 8 * s);
+        bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.np_bytes, g.np_bytes, bar_full + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -289,10 +314,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     if (lane == 0) {
       const uint64_t a_hi = desc_hi(g.RA), b_hi = desc_hi(g.S1);
       const uint32_t a_base = smem_u32(sA) >> 4;
+      const int nm = g.n_mma;
       long long T = 0;
       for (int n = 0; n < n_img; ++n) {
-        const int s = n % NUM_STAGES;
-        mbar_wait(bar_full + 8 * s, (n / NUM_STAGES) & 1, 2);
+        const int s = n % S;
+        mbar_wait(bar_full + 8 * s, (n / S) & 1, 2);
         tc_fence_after();
         const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
         for (int ch = 0; ch < g.nchunks; ++ch) {
@@ -305,29 +331,13 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((T >> 1) & 1) ^ 1), 3);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * 256;
+            const uint32_t b_base = (stage_addr + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
             uint32_t accum = 0;
-            // precision combinations: (query plane, bank plane) = (0,0) [,(1,0)] [,(0,1)]
-            const int ncomb = g.passes + g.bank_planes - 1;
-            for (int cb = 0; cb < ncomb; ++cb) {
-              const int pa = (cb == 1 && g.passes > 1) ? 1 : 0;
-              const int pb = (cb == ncomb - 1 && g.bank_planes > 1 && cb > 0) ? 1 : 0;
-              const uint32_t a_off = a_base + ((uint32_t)(pa * g.a_plane) >> 4);
-              const uint32_t b_off =
-                  (stage_addr + (uint32_t)pb * (g.img_bytes + g.tile_pad) + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
-              // the zero block sits behind the last plane: seen from plane pa its distance shrinks by pa planes
-              const uint32_t zfix = (pa && g.zero_pair) ? (((uint32_t)(pa * g.a_plane) >> 4) << 16) : 0u;
-              const int nm = g.n_mma;
 #pragma unroll 4
-              for (int t = 0; t < nm - 1; ++t) {
-                const uint2 e = sTable[t];
-                umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_off), b_hi | (uint64_t)(e.y + b_off), idesc, accum);
-                accum = 1;
-              }
-              {
-                const uint2 e = sTable[nm - 1];
-                umma_f16(d_tmem, a_hi | (uint64_t)(e.x - zfix + a_off), b_hi | (uint64_t)(e.y + b_off), idesc, accum);
-                accum = 1;
-              }
+            for (int t = 0; t < nm; ++t) {
+              const uint2 e = sTable[t];
+              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, accum);
+              accum = 1;
             }
             umma_commit(bar_tfull + 8 * buf);
           }
@@ -335,19 +345,52 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         umma_commit(bar_empty + 8 * s);
       }
     }
-  } else if (warp >= 4) {
-    // =========================== epilogue: two warpgroups, tile T handled by warpgroup T&1 from TMEM buffer T&1
-    // warpgroup wg: TMEM buffer / tile parity pr = wg & 1, column half hf = wg >> 1 (chunks hf, hf+2, ... of 16 columns)
+  } else if (warp == 2 || warp == 3) {
+    // =========================== builders: centre pixels of every candidate of the staged image, in tile order:
+    // tile (ch,vb), column r = 8*gr + rr <-> patch (u0+gr, 8*vb+rr); pairs of columns are stored side by side
+    const int bt = tid - 64;   // 0..63
+    for (int n = 0; n < n_img; ++n) {
+      const int s = n % S;
+      mbar_wait(bar_full + 8 * s, (n / S) & 1, 6);
+      const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
+      float* vt = reinterpret_cast<float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
+      int tt = 0;
+      for (int ch = 0; ch < g.nchunks; ++ch) {
+        const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
+        for (int vb = 0; vb < g.nvb; ++vb, ++tt) {
+          float* v01 = vt + (size_t)tt * g.vt_tile;
+          float* v2 = v01 + 2 * N;
+          for (int r = bt; r < N; r += 64) {
+            const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
+            float vals[3] = {0.f, 0.f, 0.f};
+            if (u < g.Ph && v < g.Pw) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const size_t go = ((size_t)(c * g.H + u + g.d) * g.W + (v + g.d)) * 16;
+                float t = __half2float(*reinterpret_cast<const __half*>(st + go));
+                if (g.bank_planes > 1)
+                  t += __half2float(*reinterpret_cast<const __half*>(st + g.img_bytes + g.tile_pad + go));
+                vals[c] = t * inv_scale;
+              }
+            }
+            const int pr = r >> 1, hf = r & 1;
+            v01[4 * pr + hf] = vals[0];
+            v01[4 * pr + 2 + hf] = vals[1];
+            v2[2 * pr + hf] = vals[2];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_vready + 8 * s);
+    }
+  } else {
+    // =========================== epilogue
+    // warpgroup wg: TMEM buffer / tile parity pr2 = wg & 1, column half hf2 = wg >> 1 (chunks hf2, hf2+2, ...)
     const int wg = (warp - 4) >> 2, q = tid - 128 - wg * 128;   // q = query row = TMEM lane
-    const int pr2 = wg & 1, hf2 = wg >> 1, q2 = q + 128 * hf2;   // q2: index inside the 256-thread pair
+    const int pr2 = wg & 1, hf2 = wg >> 1;
     const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-    // per-warpgroup column info (4 KB): bias[256] | {v0,v1} of column pairs as float4[128] | v2 pairs float2[128]
-    float* colB = reinterpret_cast<float*>(sCol) + pr2 * 1024;
-    float* colV01 = colB + 256;
-    float* colV2 = colB + 768;
-    const float c1 = CDS_LOG2E * a / beta * p.inv_scale;
-    const float cpn = -CDS_LOG2E * a * a / (2.f * beta);
+    const float c1 = CDS_LOG2E * a / beta * inv_scale;   // accumulator -> log2-unit logit
     const float2 c1c1 = make_float2(c1, c1);
     // softmax state; even / odd columns accumulate separately (packed math, shorter dependency chains)
     float m = -INFINITY;
@@ -357,100 +400,70 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     float* dbg = (p.dbg && split == 0 && qi < g.H && qj < g.W)
                      ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
                      : nullptr;
-    int u0 = 0, vb = 0;
-    bool dump = false;
-
-    auto process = [&](uint32_t* r, int c0) {
-      float2 t[8];
-      float cmax = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4 bb = *reinterpret_cast<const float4*>(colB + c0 + 4 * e);
-        t[2 * e] = fma2(make_float2(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1])), c1c1, make_float2(bb.x, bb.y));
-        t[2 * e + 1] = fma2(make_float2(__uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])), c1c1, make_float2(bb.z, bb.w));
-        cmax = max3(cmax, t[2 * e].x, t[2 * e].y);
-        cmax = max3(cmax, t[2 * e + 1].x, t[2 * e + 1].y);
-      }
-      if (dump) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int u = u0 + ((c0 + e) >> 3), v = 8 * vb + ((c0 + e) & 7);
-          if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[e]) * p.inv_scale;
-        }
-      }
-      // every weight of this chunk is < 2^-40 of the running sum's scale for all 32 queries of the warp: adding
-      // them cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
-      if (__all_sync(0xffffffffu, cmax < m - 40.f)) return;
-      if (cmax > m) {                        // rare after the first few images
-        const float sc = ex2(m - cmax);
-        const float2 sc2 = make_float2(sc, sc);
-        l2 = mul2(l2, sc2);
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc2[c] = mul2(acc2[c], sc2);
-        m = cmax;
-      }
-      const float2 nm2 = make_float2(-m, -m);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float2 ar = add2(t[e], nm2);
-        const float2 w = make_float2(ex2(ar.x), ex2(ar.y));
-        l2 = add2(l2, w);
-        const int pr = (c0 >> 1) + e;
-        if (C == 1) {
-          acc2[0] = fma2(w, *reinterpret_cast<const float2*>(colV01 + 4 * pr), acc2[0]);
-        } else {
-          const float4 v01 = *reinterpret_cast<const float4*>(colV01 + 4 * pr);
-          acc2[0] = fma2(w, make_float2(v01.x, v01.y), acc2[0]);
-          acc2[1 % C] = fma2(w, make_float2(v01.z, v01.w), acc2[1 % C]);
-          if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(colV2 + 2 * pr), acc2[2 % C]);
-        }
-      }
-    };
-
     long long T = 0;
     for (int n = 0; n < n_img; ++n) {
-      const int s = n % NUM_STAGES;
-      mbar_wait(bar_full + 8 * s, (n / NUM_STAGES) & 1, 4);
-      const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
-      const float* pn = reinterpret_cast<const float*>(st + g.pn_off);
+      const int s = n % S;
+      mbar_wait(bar_vready + 8 * s, (n / S) & 1, 4);
+      const float* vt = reinterpret_cast<const float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
-      dump = (dbg != nullptr) && n == 0;
+      const bool dump = (dbg != nullptr) && n == 0;
+      int tt = 0;
       for (int ch = 0; ch < g.nchunks; ++ch) {
-        const int N = 8 * g.chunk_g[ch];
-        u0 = g.chunk_u0[ch];
-        for (vb = 0; vb < g.nvb; ++vb, ++T) {
+        const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
+        for (int vb = 0; vb < g.nvb; ++vb, ++T, ++tt) {
           if ((int)(T & 1) != pr2) continue;
           const int buf = pr2;
-          // per-column bias and centre pixel of this tile's candidates: column r = 8*gr + rr <-> (u0+gr, 8*vb+rr)
-          bar_sync_named(1 + pr2, 256);   // everyone done reading the column info of the previous tile
-          for (int r = q2; r < N; r += 256) {
-            const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
-            const bool valid = (u < g.Ph) && (v < g.Pw);
-            colB[r] = valid ? fmaf(pn[valid ? u * g.Pw + v : 0], cpn, lw) : -INFINITY;
-            float vals[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const size_t go = ((size_t)(c * g.H + u + g.d) * g.W + (v + g.d)) * 16;
-              float t = __half2float(*reinterpret_cast<const __half*>(st + go));
-              if (g.bank_planes > 1)
-                t += __half2float(*reinterpret_cast<const __half*>(st + g.img_bytes + g.tile_pad + go));
-              vals[c] = valid ? t * p.inv_scale : 0.f;
-            }
-            const int pr = r >> 1, hf = r & 1;
-            colV01[4 * pr + hf] = vals[0];
-            colV01[4 * pr + 2 + hf] = vals[1];
-            colV2[2 * pr + hf] = vals[2];
-          }
-          bar_sync_named(1 + pr2, 256);
+          const float* v01 = vt + (size_t)tt * g.vt_tile;
+          const float* v2 = v01 + 2 * N;
           mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
           tc_fence_after();
           const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
-          // this warpgroup's 16-column chunks: hf2, hf2 + 2, ...; the partner warpgroup takes the others
           for (int c0 = 16 * hf2; c0 < N; c0 += 32) {
-            uint32_t r0[16];
-            tmem_ld16(taddr + c0, r0);
-            tmem_ld_wait16(r0);
-            process(r0, c0);
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait16(r);
+            // pass 1: best logit of the chunk (c1 > 0, so the max commutes with the affine map)
+            float dmax = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+#pragma unroll
+            for (int e = 3; e < 15; e += 2) dmax = max3(dmax, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+            dmax = fmaxf(dmax, __uint_as_float(r[15]));
+            const float cmax = fmaf(dmax, c1, lw);
+            if (dump) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int u = u0 + ((c0 + e) >> 3), v = 8 * vb + ((c0 + e) & 7);
+                if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[e]) * inv_scale;
+              }
+            }
+            // every weight of this chunk is < 2^-40 of the running max for all 32 queries of the warp: adding them
+            // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
+            if (__all_sync(0xffffffffu, cmax < m - SKIP_LOG2)) continue;
+            if (cmax > m) {                        // rare after the first few images
+              const float sc = ex2(m - cmax);
+              const float2 sc2 = make_float2(sc, sc);
+              l2 = mul2(l2, sc2);
+#pragma unroll
+              for (int c = 0; c < C; ++c) acc2[c] = mul2(acc2[c], sc2);
+              m = cmax;
+            }
+            // pass 2: weights and weighted sums
+            const float off = lw - m;
+            const float2 off2 = make_float2(off, off);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float2 ar = fma2(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), c1c1, off2);
+              const float2 w = make_float2(ex2(ar.x), ex2(ar.y));
+              l2 = add2(l2, w);
+              const int pr = (c0 >> 1) + e;
+              if (C == 1) {
+                acc2[0] = fma2(w, *reinterpret_cast<const float2*>(v01 + 4 * pr), acc2[0]);
+              } else {
+                const float4 vv = *reinterpret_cast<const float4*>(v01 + 4 * pr);
+                acc2[0] = fma2(w, make_float2(vv.x, vv.y), acc2[0]);
+                acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
+                if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(v2 + 2 * pr), acc2[2 % C]);
+              }
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -463,8 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     float l = l2.x + l2.y, acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = acc2[c].x + acc2[c].y;
-    // merge the two warpgroups' partial softmax states and write this split's partials
-    bar_sync_named(3, 128 * NUM_EPI_WG);       // column tables are dead from here on: reuse them for the merge
+    // merge the warpgroups' partial softmax states and write this split's partials
     if (wg > 0) {
       float* dst = sMerge + ((wg - 1) * 128 + q) * (2 + C);
       dst[0] = m;
@@ -472,12 +484,12 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 #pragma unroll
       for (int c = 0; c < C; ++c) dst[2 + c] = acc[c];
     }
-    bar_sync_named(3, 128 * NUM_EPI_WG);
+    bar_sync_named(1, 128 * NUM_EPI_WG);
     if (wg == 0 && qi < g.H && qj < g.W) {
       float M = m;
 #pragma unroll
       for (int w = 1; w < NUM_EPI_WG; ++w) M = fmaxf(M, sMerge[((w - 1) * 128 + q) * (2 + C)]);
-      float w0 = (m == -INFINITY) ? 0.f : ex2(m - M);
+      const float w0 = (m == -INFINITY) ? 0.f : ex2(m - M);
       float L = l * w0, A[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) A[c] = acc[c] * w0;
@@ -505,78 +517,125 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   }
 }
 
+// per-k "norm plane": granule (n,u,x) = three-way fp16 split of |p(n,u,x)|^2 arranged (ph,pm,pl,ph,pm,ph,0,0);
+// positions that are not the top-left corner of a valid k x k patch carry INVALID_NORM
+__global__ void norm_plane_kernel(const float* __restrict__ images, long long N, int C, int H, int W, int k,
+                                  uint4* __restrict__ out) {
+  const long long total = N * H * W;
+  const int Ph = H - k + 1, Pw = W - k + 1;
+  for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < total;
+       gidx += (long long)gridDim.x * blockDim.x) {
+    const int v = gidx % W, u = (gidx / W) % H;
+    const long long n = gidx / ((long long)W * H);
+    __half h[8];
+    const __half z = __float2half_rn(0.f);
+    if (u < Ph && v < Pw) {
+      const float* img = images + n * C * H * W;
+      float s = 0.f;
+      for (int c = 0; c < C; ++c)
+        for (int dy = 0; dy < k; ++dy)
+          for (int dx = 0; dx < k; ++dx) {
+            const float t = img[(c * H + u + dy) * W + v + dx];
+            s = fmaf(t, t, s);
+          }
+      const __half ph = __float2half_rn(s);
+      const __half pm = __float2half_rn(s - __half2float(ph));
+      const __half pl = __float2half_rn(s - __half2float(ph) - __half2float(pm));
+      h[0] = ph; h[1] = pm; h[2] = pl; h[3] = ph; h[4] = pm; h[5] = ph; h[6] = z; h[7] = z;
+    } else {
+      const __half big = __float2half_rn(INVALID_NORM);
+      h[0] = big; h[1] = big; h[2] = big; h[3] = z; h[4] = z; h[5] = z; h[6] = z; h[7] = z;
+    }
+    out[gidx] = *reinterpret_cast<uint4*>(h);
+  }
+}
+
 // ------------------------------------------------------------------ host side: geometry + descriptor table
+struct Gran { int a, b; };
+
+// pairs consecutive K granules of one precision combination into UMMA descriptors (K = 16 = two granules);
+// an odd tail is paired with the zero block on the query side
+int emit_pairs(const Gran* gr, int n, int a_zero, uint2* table, int nm) {
+  for (int q = 0; q < n; q += 2) {
+    if (nm >= MAX_MMAS) return -1;
+    int la, lb;
+    if (q + 1 < n) { la = gr[q + 1].a - gr[q].a; lb = gr[q + 1].b - gr[q].b; }
+    else           { la = a_zero - gr[q].a;      lb = 16; }
+    if (la <= 0 || lb <= 0 || (la >> 4) > 0x3FFF || (lb >> 4) > 0x3FFF) return -1;
+    table[nm].x = (uint32_t)(gr[q].a >> 4) | ((uint32_t)(la >> 4) << 16);
+    table[nm].y = (uint32_t)(gr[q].b >> 4) | ((uint32_t)(lb >> 4) << 16);
+    ++nm;
+  }
+  return nm;
+}
+
 int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom& g, uint2* table) {
   if (C < 1 || C > 3 || H > 32 || W > 32 || H < k || W < k || (k & 1) == 0 || k < 3) return 0;
   if (passes < 1 || passes > 2 || bank_planes < 1 || bank_planes > 2) return 0;
   g.C = C; g.H = H; g.W = W; g.k = k; g.d = k / 2;
   g.Ph = H - k + 1; g.Pw = W - k + 1;
-  g.Ppad = g.Ph * g.Pw;
-  if (g.Ppad % 4) return 0;   // norms are bulk-copied: 16-byte multiples only
   g.nb = (k + 7) / 8;
   g.RA = (k + 7) * 16;
   g.a_block = TI * g.RA;
   g.a_plane = C * g.nb * g.a_block;
-  g.a_zero = passes * g.a_plane;
+  g.a_const = passes * g.a_plane;
+  g.a_zero = g.a_const + g.a_block;
   g.a_bytes = g.a_zero + g.a_block;
   g.S1 = W * 16;
   g.img_bytes = C * H * W * 16;
+  g.np_bytes = H * W * 16;
   g.tile_pad = ((k + 8) * 16 + 127) / 128 * 128;
-  g.pn_off = bank_planes * (g.img_bytes + g.tile_pad);
-  g.stage_bytes = (g.pn_off + g.Ppad * 4 + 127) / 128 * 128;
+  g.np_off = bank_planes * (g.img_bytes + g.tile_pad);
+  g.vt_off = g.np_off + g.np_bytes + g.tile_pad;
   g.passes = passes; g.bank_planes = bank_planes;
   // patch-row chunks: N = 8*G <= 256, G even (UMMA M=128 needs N % 16 == 0)
-  int rows = g.Ph, u0 = 0;
+  int rows = g.Ph, u0 = 0, gmax = 0;
   g.nchunks = 0;
   while (rows > 0) {
     if (g.nchunks == MAX_CHUNKS) return 0;
-    int G = rows > 32 ? 32 : rows;
+    const int G = rows > 32 ? 32 : rows;
     int Ge = (G + 1) & ~1;
     if (Ge < 2) Ge = 2;
     g.chunk_u0[g.nchunks] = u0; g.chunk_g[g.nchunks] = Ge;
+    if (Ge > gmax) gmax = Ge;
     ++g.nchunks; u0 += G; rows -= G;
   }
   g.nvb = (g.Pw + 7) / 8;
   // a rounded-up last patch row must stay inside the strip array: u + 8*(nb-1) <= H-1
   if (g.chunk_u0[g.nchunks - 1] + g.chunk_g[g.nchunks - 1] - 1 + 8 * (g.nb - 1) > H - 1) return 0;
-  // K granule list (c, blk, dx); pairs (dx,dx+1) inside a block, leftovers paired across blocks, last with zeros
-  struct Gran { int a, b; };
+  g.vt_tile = 8 * gmax / 2 * 6;                      // floats per tile: N/2 pairs x (4 + 2)
+  const int vt_bytes = g.nchunks * g.nvb * g.vt_tile * 4;
+  g.stage_bytes = (g.vt_off + vt_bytes + 127) / 128 * 128;
+
+  // K granule lists per precision combination (query plane, bank plane): (0,0)+norm granule [, (1,0)] [, (0,1)]
+  Gran gr[3 * 4 * 32 + 2];
   int nm = 0;
-  Gran left[64]; int nleft = 0;
-  for (int c = 0; c < C; ++c)
-    for (int blk = 0; blk < g.nb; ++blk) {
-      const int a0 = (c * g.nb + blk) * g.a_block, b0 = (c * H + 8 * blk) * g.S1;
-      int dx = 0;
-      for (; dx + 1 < k; dx += 2) {
-        if (nm >= MAX_MMAS) return 0;
-        table[nm].x = (uint32_t)((a0 + dx * 16) >> 4) | (1u << 16);   // LBO = 16 B
-        table[nm].y = (uint32_t)((b0 + dx * 16) >> 4) | (1u << 16);
-        ++nm;
-      }
-      if (dx < k) { left[nleft].a = a0 + dx * 16; left[nleft].b = b0 + dx * 16; ++nleft; }
-    }
-  g.zero_pair = nleft & 1;
-  for (int q = 0; q < nleft; q += 2) {
-    if (nm >= MAX_MMAS) return 0;
-    if (q + 1 < nleft) {
-      table[nm].x = (uint32_t)(left[q].a >> 4) | ((uint32_t)((left[q + 1].a - left[q].a) >> 4) << 16);
-      table[nm].y = (uint32_t)(left[q].b >> 4) | ((uint32_t)((left[q + 1].b - left[q].b) >> 4) << 16);
-    } else {
-      // second K granule: zeros on the query side (A), any finite bank data on the B side
-      table[nm].x = (uint32_t)(left[q].a >> 4) | ((uint32_t)((g.a_zero - left[q].a) >> 4) << 16);
-      table[nm].y = (uint32_t)(left[q].b >> 4) | (1u << 16);
-    }
-    ++nm;
+  for (int cb = 0; cb < passes + bank_planes - 1; ++cb) {
+    const int pa = (cb == 1 && passes > 1) ? 1 : 0;
+    const int pb = (cb > 0 && !pa) ? 1 : 0;
+    int n = 0;
+    for (int c = 0; c < C; ++c)
+      for (int blk = 0; blk < g.nb; ++blk)
+        for (int dx = 0; dx < k; ++dx) {
+          gr[n].a = pa * g.a_plane + (c * g.nb + blk) * g.a_block + dx * 16;
+          gr[n].b = pb * (g.img_bytes + g.tile_pad) + (c * H + 8 * blk) * g.S1 + dx * 16;
+          ++n;
+        }
+    if (cb == 0) { gr[n].a = g.a_const; gr[n].b = g.np_off; ++n; }
+    nm = emit_pairs(gr, n, g.a_zero, table, nm);
+    if (nm < 0) return 0;
   }
   g.n_mma = nm;
   g.smem_A = (g.a_bytes + 1023) / 1024 * 1024;
-  g.smem_stage = NUM_STAGES * g.stage_bytes;
-  g.smem_colinfo = 2 * 256 * 16;
+  g.smem_merge = ((NUM_EPI_WG - 1) * 128 * 5 * 4 + 127) / 128 * 128;
   g.smem_table = (nm * 8 + 127) / 128 * 128;
-  g.smem_bar = 8 * (2 * NUM_STAGES + 4) + 16 + 64;
-  g.smem_total = g.smem_A + g.smem_stage + g.smem_colinfo + g.smem_table + g.smem_bar + 1024;
+  g.smem_bar = 8 * 10 + 16 + 32;
+  const int fixed = g.smem_A + g.smem_merge + g.smem_table + g.smem_bar + 1024;
+  g.stages = MAX_STAGES;
+  while (g.stages > 1 && fixed + g.stages * g.stage_bytes > 227 * 1024) --g.stages;
+  g.smem_stage = g.stages * g.stage_bytes;
+  g.smem_total = fixed + g.smem_stage;
   if (g.smem_total > 227 * 1024) return 0;
-  // the zero-block LBO (a_zero - a) must fit 14 bits of 16-byte units: a_bytes < 256 KB always holds here
   return 1;
 }
 
@@ -588,8 +647,19 @@ extern "C" int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passe
   return make_geom(C, H, W, k, passes, bank_planes, g, local) ? g.smem_total : 0;
 }
 
+extern "C" int cds_pack_norm_plane(const float* images, int64_t N, int C, int H, int W, int k, void* out_f16,
+                                   void* stream) {
+  CDS_CHECK_ARG(N >= 1 && k >= 1 && k <= H && k <= W, "cds_pack_norm_plane: bad arguments");
+  const long long total = (long long)N * H * W;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads > 148 * 32 ? 148 * 32 : (total + threads - 1) / threads);
+  norm_plane_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(images, N, C, H, W, k, (uint4*)out_f16);
+  CDS_CHECK_LAUNCH("norm_plane_kernel");
+  return CDS_OK;
+}
+
 extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
-                                     const void* bank_hi, const void* bank_lo, float bank_scale, const float* pnorm,
+                                     const void* bank_hi, const void* bank_lo, float bank_scale, const void* norm_plane,
                                      const int32_t* idx, const float* logw, int64_t n_sel, int splits, int passes,
                                      float* m, float* l, float* acc, float* dbg_dots, void* stream) {
   UmmaParams p;
@@ -604,8 +674,9 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
   p.B = B; p.pad = query_pad; p.splits = splits; p.n_sel = n_sel;
   p.x = x; p.beta = beta;
   p.bank_hi = (const uint8_t*)bank_hi; p.bank_lo = (const uint8_t*)bank_lo;
-  p.inv_scale = 1.f / bank_scale;
-  p.pnorm = pnorm; p.idx = idx; p.logw = logw;
+  p.norm_plane = (const uint8_t*)norm_plane;
+  p.scale = bank_scale;
+  p.idx = idx; p.logw = logw;
   p.m = m; p.l = l; p.acc = acc; p.dbg = dbg_dots;
   const int tiles = ((H + TI - 1) / TI) * ((W + TJ - 1) / TJ);
   dim3 grid(tiles, splits, B);

@@ -99,7 +99,7 @@ class ScoreEngine:
         b = self.bank
         B = x.shape[0]
         hi, lo, scale = b.strip8()
-        pn = b.patch_norms(k)
+        pn = b.norm_plane(k)
         tiles = ((b.H + 15) // 16) * ((b.W + 7) // 8)
         S = self._splits(tiles, B, n_sel)
         P = self._partials(tag, S, B)

@@ -50,6 +50,12 @@ int cds_pack_strip8(const float* images, int64_t N, int C, int H, int W, float s
 /* ||p||^2 of every valid (un-padded) k x k x C patch: out[n][H-k+1][W-k+1]  (idealscore.py:451,243) */
 int cds_patch_norms(const float* images, int64_t N, int C, int H, int W, int k, float* out, void* stream);
 
+/* Per-k "norm plane" for the tensor-core kernel: out[n][u][x][8] (fp16), granule = three-way fp16 split of
+ * ||p(n,u,x)||^2 (patch with top-left corner (u,x)) laid out (ph,pm,pl,ph,pm,ph,0,0); positions that are not a
+ * valid patch carry a large marker so they vanish in the softmax.  It is contracted against the constant
+ * -a*scale/2 inside the same UMMA K loop, i.e. the a^2|p|^2 term of idealscore.py:456 costs one K granule. */
+int cds_pack_norm_plane(const float* images, int64_t N, int C, int H, int W, int k, void* out_f16, void* stream);
+
 /* ---- score partials (the hot path) */
 
 /* Exact fp32 SIMT evaluation of the unified masked-softmax form for LS / ELS / bbELS.
@@ -68,7 +74,7 @@ int cds_partials_simt(int kind, int query_pad, const float* x, int B, int C, int
  * first selected image (tests only, may be NULL). */
 int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k,
                           const float* beta, const void* bank_hi, const void* bank_lo, float bank_scale,
-                          const float* pnorm, const int32_t* idx, const float* logw, int64_t n_sel,
+                          const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
                           int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
                           void* stream);
 /* dynamic shared memory the umma kernel needs for this geometry (0 = unsupported geometry) */

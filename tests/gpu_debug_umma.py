@@ -45,6 +45,9 @@ def main():
         print(f"   kernel returned in {time.time() - t0:.3f}s", flush=True)
         for b in range(2):
             ref = dots_ref(x[b].cpu().double().numpy(), imgs[0].double().numpy(), k, pad)
+            # the accumulator also carries the norm term: scale*(q.p) - (a*scale/2)|p|^2  (reported / scale)
+            pn = bank.patch_norms(k).view(-1, P)[0].cpu().double().numpy()
+            ref = ref - 0.5 * np.sqrt(1 - float(beta[b])) * pn[None, :]
             got = dbg[b].cpu().double().numpy()
             err = np.abs(got - ref)
             print(f"   b={b} dots: nan={np.isnan(got).sum()} max|err|={np.nanmax(err):.3e} ref_rms={ref.std():.3f}",
