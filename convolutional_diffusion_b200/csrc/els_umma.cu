@@ -185,6 +185,13 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// one lane of a converged warp (the warp stays converged around it, so descriptors live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.b32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -213,7 +220,6 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   uint8_t* sA = smem;
   uint8_t* sStage = smem + g.smem_A;
   float* sMerge = reinterpret_cast<float*>(smem + g.smem_A + g.smem_stage);           // [NUM_EPI_WG-1][128][2+C]
-  uint2* sTable = reinterpret_cast<uint2*>(smem + g.smem_A + g.smem_stage + g.smem_merge);
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + g.smem_A + g.smem_stage + g.smem_merge + g.smem_table);
   // barriers: full[2], empty[2], vready[2], tfull[2], tempty[2]; then the TMEM base address
   const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 16, bar_vready = bar_full + 32;
@@ -238,7 +244,6 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
-  for (int e = tid; e < g.n_mma; e += THREADS) sTable[e] = p.table[e];
   // zero guards behind every staged tile (over-reads of masked columns must stay finite)
   for (int s = 0; s < S; ++s)
     for (int pl = 0; pl <= g.bank_planes; ++pl) {
@@ -310,40 +315,46 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (single thread)
-    if (lane == 0) {
-      const uint64_t a_hi = desc_hi(g.RA), b_hi = desc_hi(g.S1);
-      const uint32_t a_base = smem_u32(sA) >> 4;
-      const int nm = g.n_mma;
-      long long T = 0;
-      for (int n = 0; n < n_img; ++n) {
-        const int s = n % S;
-        mbar_wait(bar_full + 8 * s, (n / S) & 1, 2);
-        tc_fence_after();
-        const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
-        for (int ch = 0; ch < g.nchunks; ++ch) {
-          const uint32_t N = 8u * g.chunk_g[ch];
-          // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
-          // N>>3 at [17,23), M>>4 at [24,29)
-          const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
-          for (int vb = 0; vb < g.nvb; ++vb, ++T) {
-            const int buf = (int)(T & 1);
-            mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((T >> 1) & 1) ^ 1), 3);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * 256;
-            const uint32_t b_base = (stage_addr + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
-            uint32_t accum = 0;
+    // =========================== MMA issuer: the warp stays converged, one elected lane issues.  The descriptor
+    // table is read from the kernel parameters (constant bank) with warp-uniform indices, so descriptor arithmetic
+    // runs on the uniform datapath.
+    const uint64_t a_hi = desc_hi(g.RA), b_hi = desc_hi(g.S1);
+    const uint32_t a_base = smem_u32(sA) >> 4;
+    const int nm = g.n_mma;
+    long long T = 0;
+    for (int n = 0; n < n_img; ++n) {
+      const int s = n % S;
+      mbar_wait(bar_full + 8 * s, (n / S) & 1, 2);
+      tc_fence_after();
+      const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
+      for (int ch = 0; ch < g.nchunks; ++ch) {
+        const uint32_t N = 8u * g.chunk_g[ch];
+        // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
+        // N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+        for (int vb = 0; vb < g.nvb; ++vb, ++T) {
+          const int buf = (int)(T & 1);
+          mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((T >> 1) & 1) ^ 1), 3);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * 256;
+          const uint32_t b_base = (stage_addr + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
+          if (elect_one()) {
+            {
+              const uint2 e = p.table[0];
+              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 0u);
+            }
 #pragma unroll 4
-            for (int t = 0; t < nm; ++t) {
-              const uint2 e = sTable[t];
-              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, accum);
-              accum = 1;
+            for (int t = 1; t < nm; ++t) {
+              const uint2 e = p.table[t];
+              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 1u);
             }
             umma_commit(bar_tfull + 8 * buf);
           }
+          __syncwarp();
         }
-        umma_commit(bar_empty + 8 * s);
       }
+      if (elect_one()) umma_commit(bar_empty + 8 * s);
+      __syncwarp();
     }
   } else if (warp == 2 || warp == 3) {
     // =========================== builders: centre pixels of every candidate of the staged image, in tile order:
@@ -418,10 +429,21 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
           tc_fence_after();
           const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
+          const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
+          // partial blocks inside the row and rounded-up patch rows are already masked by the norm plane's marker;
+          // explicit masking is only needed when an 8-column block runs past the end of the image row
+          const bool edge = 8 * vb + 8 > g.W;
           for (int c0 = 16 * hf2; c0 < N; c0 += 32) {
             uint32_t r[16];
             tmem_ld16(taddr + c0, r);
             tmem_ld_wait16(r);
+            // columns that are not valid patches (partial last 8-column block, rounded-up last patch row) are
+            // forced to -FLT_MAX: they never win the max and get weight 0.  Warp-uniform, only in edge tiles.
+            if (edge) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (((c0 + e) & 7) >= nval_v || ((c0 + e) >> 3) >= nval_u) r[e] = 0xff7fffffu;
+            }
             // pass 1: best logit of the chunk (c1 > 0, so the max commutes with the affine map)
             float dmax = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
 #pragma unroll
