@@ -94,6 +94,25 @@ class ScoreEngine:
         self.launches += 1
         return P
 
+    def ls_supported(self, k):
+        b = self.bank
+        d = k // 2
+        smem = 4 * 4 * (b.H * (b.W + 2 * d) + (b.H + 2 * d) * b.W)
+        return b.C in (1, 3) and b.H * b.W <= 4096 and smem <= 227 * 1024
+
+    def ls_partials(self, x, beta, k, sel, tag="ls"):
+        """Bank-streaming LS kernel (csrc/ls_kernel.cu): the bank slice of every CTA is read once."""
+        idx, logw, n_sel = sel
+        b = self.bank
+        B = x.shape[0]
+        S = int(min(n_sel, max(1, (2 * sm_count(self.device)) // ((B + 3) // 4))))
+        P = self._partials(tag, S, B)
+        _lib.check(self.lib.cds_ls_partials(_lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(b.images),
+                                            _lib.ptr(idx), _lib.ptr(logw), n_sel, S, _lib.ptr(P.m), _lib.ptr(P.l),
+                                            _lib.ptr(P.acc), _lib.stream_ptr()), "cds_ls_partials")
+        self.launches += 1
+        return P
+
     def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma"):
         idx, logw, n_sel = sel
         b = self.bank
@@ -150,8 +169,11 @@ class ScoreEngine:
         if kind == "bbELS" and k >= b.H:          # idealscore.py:163-164: delegate to the internal LS module
             kind, sel = "LS", (sel_ls if sel_ls is not None else sel)
         if kind == "LS":
-            P = self.combine(self.simt_partials("LS", "zeros", x, beta, k, sel))
-            self.finalize(P, x, beta, mu, score)
+            if self.use_tensor_cores and self.ls_supported(k):
+                P = self.ls_partials(x, beta, k, sel)
+            else:
+                P = self.simt_partials("LS", "zeros", x, beta, k, sel)
+            self.finalize(self.combine(P), x, beta, mu, score)
         elif kind == "ELS":
             if k > b.H or k > b.W:
                 raise ValueError(f"ELS needs kernel size <= image size, got k={k} for {b.H}x{b.W}")

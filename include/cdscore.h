@@ -67,6 +67,13 @@ int cds_partials_simt(int kind, int query_pad, const float* x, int B, int C, int
                       const float* beta, const float* images, const int32_t* idx, const float* logw,
                       int64_t n_sel, int splits, int region, float* m, float* l, float* acc, void* stream);
 
+/* LS (idealscore.py:497-557) as a bank-streaming kernel: the selected images are read from HBM exactly once per
+ * launch, squared differences are box-summed separably in shared memory, every thread carries the online softmax of
+ * its pixels.  Same partial layout as cds_partials_simt(kind = LS); C in {1,3}, H*W <= 4096. */
+int cds_ls_partials(const float* x, int B, int C, int H, int W, int k, const float* beta, const float* images,
+                    const int32_t* idx, const float* logw, int64_t n_sel, int splits, float* m, float* l, float* acc,
+                    void* stream);
+
 /* tcgen05 / TMEM evaluation of ELS (and the bbELS centre region): queries = all H*W pixels of x padded
  * per query_pad, candidates = every valid k x k patch of the selected images, streamed from the strip8
  * bank by bulk-async copies.  passes = 1: fp16 query; 2: fp16 hi+lo query (fp32-grade dot products for
