@@ -13,7 +13,8 @@
 
 namespace {
 
-constexpr int IB = 4;      // images per shared-memory round
+// images per shared-memory round (amortises the three block barriers); fewer for RGB to bound the registers
+__host__ __device__ constexpr int images_per_round(int C) { return C == 1 ? 8 : 4; }
 constexpr int SB = 4;      // samples per CTA (softmax states held in registers)
 constexpr int MAXPPT = 4;  // pixels per thread (H*W <= 4096)
 
@@ -31,6 +32,7 @@ struct LsParams {
 template <int C, int PPT>
 __global__ void __launch_bounds__(PPT == 2 ? 512 : 1024) ls_partials_kernel(LsParams p) {
   extern __shared__ float smem[];
+  constexpr int IB = images_per_round(C);
   const int H = p.H, W = p.W, k = p.k, d = k / 2, HW = H * W;
   const int Wp = W + 2 * d, Hp = H + 2 * d;
   float* e_map = smem;                       // [IB][H][Wp]   squared differences, zero columns left/right
@@ -103,31 +105,57 @@ __global__ void __launch_bounds__(PPT == 2 ? 512 : 1024) ls_partials_kernel(LsPa
             e_map[(ib * H + py[j]) * Wp + px[j] + d] = e;
           }
       __syncthreads();
-      // (2) horizontal window sums
+      // (2) horizontal window sums: the IB images advance together, so IB independent loads are in flight
 #pragma unroll
-      for (int ib = 0; ib < IB; ++ib)
+      for (int j = 0; j < PPT; ++j)
+        if (act[j]) {
+          const float* row = e_map + py[j] * Wp + px[j];
+          float r[IB];
 #pragma unroll
-        for (int j = 0; j < PPT; ++j)
-          if (act[j]) {
-            const float* row = e_map + (ib * H + py[j]) * Wp + px[j];
-            float r = 0.f;
-            for (int dx = 0; dx < k; ++dx) r += row[dx];
-            r_map[(ib * Hp + py[j] + d) * W + px[j]] = r;
-          }
+          for (int ib = 0; ib < IB; ++ib) r[ib] = 0.f;
+#pragma unroll 2
+          for (int dx = 0; dx < k; ++dx)
+#pragma unroll
+            for (int ib = 0; ib < IB; ++ib) r[ib] += row[ib * H * Wp + dx];
+#pragma unroll
+          for (int ib = 0; ib < IB; ++ib) r_map[(ib * Hp + py[j] + d) * W + px[j]] = r[ib];
+        }
       __syncthreads();
       // (3) vertical window sums -> logits -> online softmax
 #pragma unroll
-      for (int ib = 0; ib < IB; ++ib) {
-        if (ib >= ni) break;
+      for (int j = 0; j < PPT; ++j)
+        if (act[j]) {
+          const float* col = r_map + py[j] * W + px[j];
+          float box[IB];
 #pragma unroll
-        for (int j = 0; j < PPT; ++j)
-          if (act[j]) {
-            const float* col = r_map + (ib * Hp + py[j]) * W + px[j];
-            float box = 0.f;
-            for (int dy = 0; dy < k; ++dy) box += col[dy * W];
-            sm[s][j].push(fmaf(box, sc_s[s], lw[ib]), tv[ib][j]);
+          for (int ib = 0; ib < IB; ++ib) box[ib] = 0.f;
+#pragma unroll 2
+          for (int dy = 0; dy < k; ++dy)
+#pragma unroll
+            for (int ib = 0; ib < IB; ++ib) box[ib] += col[(ib * Hp + dy) * W];
+          // one max / one rescale for the whole round instead of a branch per image
+          float t[IB], tmax = -INFINITY;
+#pragma unroll
+          for (int ib = 0; ib < IB; ++ib) {
+            t[ib] = ib < ni ? fmaf(box[ib], sc_s[s], lw[ib]) : -INFINITY;
+            tmax = fmaxf(tmax, t[ib]);
           }
-      }
+          Softmax2<C>& st = sm[s][j];
+          if (tmax > st.m) {
+            const float scl = exp2f(st.m - tmax);
+            st.l *= scl;
+#pragma unroll
+            for (int c = 0; c < C; ++c) st.acc[c] *= scl;
+            st.m = tmax;
+          }
+#pragma unroll
+          for (int ib = 0; ib < IB; ++ib) {
+            const float w = exp2f(t[ib] - st.m);
+            st.l += w;
+#pragma unroll
+            for (int c = 0; c < C; ++c) st.acc[c] = fmaf(w, tv[ib][j][c], st.acc[c]);
+          }
+        }
       __syncthreads();
     }
   }
@@ -178,7 +206,7 @@ extern "C" int cds_ls_partials(const float* x, int B, int C, int H, int W, int k
   if (C == 3 && ppt < 2 && HW > 512) ppt = 2;          // keep the register footprint of tv[IB][PPT][C] in check
   const int threads = ((HW + ppt - 1) / ppt + 31) / 32 * 32;
   LsParams p{B, C, H, W, k, splits, ppt, (long long)n_sel, x, beta, images, idx, logw, m, l, acc};
-  const size_t smem = (size_t)IB * (H * (W + 2 * d) + (H + 2 * d) * W) * sizeof(float);
+  const size_t smem = (size_t)images_per_round(C) * (H * (W + 2 * d) + (H + 2 * d) * W) * sizeof(float);
   CDS_CHECK_ARG(smem <= 227 * 1024, "cds_ls_partials: kernel size %d too large for shared memory", k);
   dim3 grid(splits, (B + SB - 1) / SB);
   int rc = C == 1 ? launch_ls<1>(p, smem, grid, threads, (cudaStream_t)stream)

@@ -158,25 +158,49 @@ __global__ void patch_norms_kernel(const float* __restrict__ images, long long N
   }
 }
 
+// log-sum-exp merge of S slices: 32 pixels x 8 slice groups per block; each group folds its slices online, the
+// groups are then merged through shared memory (S reaches ~300 for the LS kernel, so a serial loop would be latency bound)
+constexpr int CMB_G = 8;
 __global__ void combine_kernel(const float* __restrict__ m, const float* __restrict__ l, const float* __restrict__ acc,
                                int S, int B, int C, int HW, float* m_out, float* l_out, float* acc_out) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= B * HW) return;
-  const int b = g / HW, pix = g % HW;
-  float M = -INFINITY;
-  for (int s = 0; s < S; ++s) M = fmaxf(M, m[((size_t)s * B + b) * HW + pix]);
-  float L = 0.f, A[8];
+  __shared__ float sh[CMB_G][32][10];
+  const int lane = threadIdx.x, grp = threadIdx.y;
+  const int g = blockIdx.x * 32 + lane;
+  const bool on = g < B * HW;
+  const int b = on ? g / HW : 0, pix = on ? g % HW : 0;
+  float M = -INFINITY, L = 0.f, A[8];
   for (int c = 0; c < C; ++c) A[c] = 0.f;
-  for (int s = 0; s < S; ++s) {
-    const size_t o = ((size_t)s * B + b) * HW + pix;
-    const float ms = m[o];
-    const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
-    L = fmaf(l[o], w, L);
-    for (int c = 0; c < C; ++c) A[c] = fmaf(acc[(((size_t)s * B + b) * C + c) * HW + pix], w, A[c]);
+  if (on) {
+    for (int s = grp; s < S; s += CMB_G) {
+      const size_t o = ((size_t)s * B + b) * HW + pix;
+      const float ms = m[o];
+      if (ms == -INFINITY) continue;
+      const float Mn = fmaxf(M, ms);
+      const float w0 = exp2f(M - Mn), w1 = exp2f(ms - Mn);
+      L = L * w0 + l[o] * w1;
+      for (int c = 0; c < C; ++c) A[c] = A[c] * w0 + acc[(((size_t)s * B + b) * C + c) * HW + pix] * w1;
+      M = Mn;
+    }
   }
-  m_out[(size_t)b * HW + pix] = M;
-  l_out[(size_t)b * HW + pix] = L;
-  for (int c = 0; c < C; ++c) acc_out[((size_t)b * C + c) * HW + pix] = A[c];
+  sh[grp][lane][0] = M;
+  sh[grp][lane][1] = L;
+  for (int c = 0; c < C; ++c) sh[grp][lane][2 + c] = A[c];
+  __syncthreads();
+  if (grp == 0 && on) {
+    float Mt = -INFINITY;
+    for (int q = 0; q < CMB_G; ++q) Mt = fmaxf(Mt, sh[q][lane][0]);
+    float Lt = 0.f, At[8];
+    for (int c = 0; c < C; ++c) At[c] = 0.f;
+    for (int q = 0; q < CMB_G; ++q) {
+      const float mq = sh[q][lane][0];
+      const float w = (mq == -INFINITY) ? 0.f : exp2f(mq - Mt);
+      Lt = fmaf(sh[q][lane][1], w, Lt);
+      for (int c = 0; c < C; ++c) At[c] = fmaf(sh[q][lane][2 + c], w, At[c]);
+    }
+    m_out[(size_t)b * HW + pix] = Mt;
+    l_out[(size_t)b * HW + pix] = Lt;
+    for (int c = 0; c < C; ++c) acc_out[((size_t)b * C + c) * HW + pix] = At[c];
+  }
 }
 
 __global__ void finalize_kernel(const float* __restrict__ x, const float* __restrict__ beta, const float* __restrict__ l,
@@ -265,8 +289,8 @@ extern "C" int cds_patch_norms(const float* images, int64_t N, int C, int H, int
 extern "C" int cds_combine(const float* m, const float* l, const float* acc, int S, int B, int C, int HW, float* m_out,
                            float* l_out, float* acc_out, void* stream) {
   CDS_CHECK_ARG(S >= 1 && C <= 8, "cds_combine: bad S=%d C=%d", S, C);
-  const int threads = 128, blocks = (B * HW + threads - 1) / threads;
-  combine_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(m, l, acc, S, B, C, HW, m_out, l_out, acc_out);
+  const int blocks = (B * HW + 31) / 32;
+  combine_kernel<<<blocks, dim3(32, CMB_G), 0, (cudaStream_t)stream>>>(m, l, acc, S, B, C, HW, m_out, l_out, acc_out);
   CDS_CHECK_LAUNCH("combine_kernel");
   return CDS_OK;
 }

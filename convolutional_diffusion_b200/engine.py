@@ -97,7 +97,7 @@ class ScoreEngine:
     def ls_supported(self, k):
         b = self.bank
         d = k // 2
-        smem = 4 * 4 * (b.H * (b.W + 2 * d) + (b.H + 2 * d) * b.W)
+        smem = (8 if b.C == 1 else 4) * 4 * (b.H * (b.W + 2 * d) + (b.H + 2 * d) * b.W)   # images per round
         return b.C in (1, 3) and b.H * b.W <= 4096 and smem <= 227 * 1024
 
     def ls_partials(self, x, beta, k, sel, tag="ls"):
