@@ -32,6 +32,7 @@ SIGNATURES = {
                                    _p, _p, _p, _p, _p]),
     "cds_els_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
     "cds_combine": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "cds_combine_packed": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "cds_finalize": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "cds_ddim_step": (_i, [_p, _p, _p, _p, _i, _i64, _p]),
 }

@@ -162,7 +162,8 @@ __global__ void patch_norms_kernel(const float* __restrict__ images, long long N
 // groups are then merged through shared memory (S reaches ~300 for the LS kernel, so a serial loop would be latency bound)
 constexpr int CMB_G = 8;
 __global__ void combine_kernel(const float* __restrict__ m, const float* __restrict__ l, const float* __restrict__ acc,
-                               int S, int B, int C, int HW, float* m_out, float* l_out, float* acc_out) {
+                               int S, int B, int C, int HW, size_t stride_ml, size_t stride_acc, float* m_out,
+                               float* l_out, float* acc_out) {
   __shared__ float sh[CMB_G][32][10];
   const int lane = threadIdx.x, grp = threadIdx.y;
   const int g = blockIdx.x * 32 + lane;
@@ -172,13 +173,13 @@ __global__ void combine_kernel(const float* __restrict__ m, const float* __restr
   for (int c = 0; c < C; ++c) A[c] = 0.f;
   if (on) {
     for (int s = grp; s < S; s += CMB_G) {
-      const size_t o = ((size_t)s * B + b) * HW + pix;
+      const size_t o = (size_t)s * stride_ml + (size_t)b * HW + pix;
       const float ms = m[o];
       if (ms == -INFINITY) continue;
       const float Mn = fmaxf(M, ms);
       const float w0 = exp2f(M - Mn), w1 = exp2f(ms - Mn);
       L = L * w0 + l[o] * w1;
-      for (int c = 0; c < C; ++c) A[c] = A[c] * w0 + acc[(((size_t)s * B + b) * C + c) * HW + pix] * w1;
+      for (int c = 0; c < C; ++c) A[c] = A[c] * w0 + acc[(size_t)s * stride_acc + ((size_t)b * C + c) * HW + pix] * w1;
       M = Mn;
     }
   }
@@ -290,8 +291,21 @@ extern "C" int cds_combine(const float* m, const float* l, const float* acc, int
                            float* l_out, float* acc_out, void* stream) {
   CDS_CHECK_ARG(S >= 1 && C <= 8, "cds_combine: bad S=%d C=%d", S, C);
   const int blocks = (B * HW + 31) / 32;
-  combine_kernel<<<blocks, dim3(32, CMB_G), 0, (cudaStream_t)stream>>>(m, l, acc, S, B, C, HW, m_out, l_out, acc_out);
+  combine_kernel<<<blocks, dim3(32, CMB_G), 0, (cudaStream_t)stream>>>(m, l, acc, S, B, C, HW, (size_t)B * HW,
+                                                                       (size_t)B * C * HW, m_out, l_out, acc_out);
   CDS_CHECK_LAUNCH("combine_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_combine_packed(const float* packed, int S, int B, int C, int HW, float* m_out, float* l_out,
+                                  float* acc_out, void* stream) {
+  CDS_CHECK_ARG(S >= 1 && C <= 8, "cds_combine_packed: bad S=%d C=%d", S, C);
+  const size_t slice = (size_t)B * (2 + C) * HW;     // one rank's [m | l | acc]
+  const int blocks = (B * HW + 31) / 32;
+  combine_kernel<<<blocks, dim3(32, CMB_G), 0, (cudaStream_t)stream>>>(packed, packed + (size_t)B * HW,
+                                                                       packed + (size_t)2 * B * HW, S, B, C, HW, slice,
+                                                                       slice, m_out, l_out, acc_out);
+  CDS_CHECK_LAUNCH("combine_kernel(packed)");
   return CDS_OK;
 }
 

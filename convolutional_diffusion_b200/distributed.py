@@ -28,15 +28,26 @@ def gather_partials(m, l, acc, group=None):
     return out
 
 
-def allgather_combine(engine, P):
-    """Merge slice 0 of every rank's partials into slice 0 of P, identically on all ranks."""
+def allgather_combine(engine, P, local_S):
+    """Merge the local_S CTA slices of this rank into a packed [m | l | acc] record, all-gather the records (ONE
+    collective, (2+C)*B*HW floats per rank) and merge them in rank order into slice 0 of P, identically on all ranks.
+    Buffers are cached so the sequence is CUDA-graph capturable."""
     group = engine.group
-    gm, gl, gacc = gather_partials(P.m[0], P.l[0], P.acc[0], group)
-    world = gm.shape[0]
-    _lib.check(engine.lib.cds_combine(_lib.ptr(gm), _lib.ptr(gl), _lib.ptr(gacc), world, P.B, P.C, P.HW,
-                                      _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), _lib.stream_ptr()),
-               "cds_combine")
-    engine.launches += 1
+    world = dist.get_world_size(group)
+    key = ("packed", P.B)
+    if key not in engine._buf:
+        n = P.B * (2 + P.C) * P.HW
+        engine._buf[key] = (torch.empty(n, dtype=torch.float32, device=P.m.device),
+                            torch.empty(world * n, dtype=torch.float32, device=P.m.device))
+    mine, gathered = engine._buf[key]
+    bhw = P.B * P.HW
+    _lib.check(engine.lib.cds_combine(_lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), local_S, P.B, P.C, P.HW,
+                                      _lib.ptr(mine), _lib.ptr(mine[bhw:]), _lib.ptr(mine[2 * bhw:]),
+                                      _lib.stream_ptr()), "cds_combine")
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    _lib.check(engine.lib.cds_combine_packed(_lib.ptr(gathered), world, P.B, P.C, P.HW, _lib.ptr(P.m), _lib.ptr(P.l),
+                                             _lib.ptr(P.acc), _lib.stream_ptr()), "cds_combine_packed")
+    engine.launches += 2
     return P
 
 

@@ -132,14 +132,14 @@ class ScoreEngine:
 
     def combine(self, P):
         """Merge the S slices into slice 0 (in place), then across ranks when the bank is sharded."""
+        if self.group is not None:
+            from .distributed import allgather_combine
+            return allgather_combine(self, P, P.S)
         if P.S > 1:
             _lib.check(self.lib.cds_combine(_lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), P.S, P.B, P.C, P.HW,
                                             _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), _lib.stream_ptr()),
                        "cds_combine")
             self.launches += 1
-        if self.group is not None:
-            from .distributed import allgather_combine
-            allgather_combine(self, P)
         return P
 
     def finalize(self, P, x, beta, mu, score, region=0, d=0):

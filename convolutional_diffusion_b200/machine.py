@@ -117,7 +117,7 @@ class ScheduledScoreMachine(nn.Module):
         shuffled = mod.shuffle or (mod.kind == "LS" and mod._ls_shuffles()) or needs_ls and mod._ls_shuffles()
         key = (nsteps, B, label, tuple(self.scales) if self.scales is not None else None)
         with torch.cuda.device(eng.device):
-            if record is not None or not self.use_cuda_graph or shuffled or eng.group is not None:
+            if record is not None or not self.use_cuda_graph or shuffled:
                 xw = x.to(eng.device, torch.float32).clone().contiguous()
                 mu = torch.empty_like(xw)
                 self._run_steps(eng, self._plan(nsteps, B, eng.device), xw, mu, sel, sel_ls, record)

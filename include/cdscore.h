@@ -93,6 +93,11 @@ int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passes, int bank
 int cds_combine(const float* m, const float* l, const float* acc, int S, int B, int C, int HW,
                 float* m_out, float* l_out, float* acc_out, void* stream);
 
+/* the same merge for S slices that each sit packed as [m | l | acc] (B*(2+C)*HW floats): the layout one rank
+ * contributes to the all-gather when the bank is sharded across GPUs, so the exchange is ONE collective */
+int cds_combine_packed(const float* packed, int S, int B, int C, int HW, float* m_out, float* l_out, float* acc_out,
+                       void* stream);
+
 /* mu = acc/l ; score = -(x - sqrt(1-beta) mu)/beta  (idealscore.py:372,473,557).
  * region: 0 = all pixels, 1 = only pixels with d<=i<H-d and d<=j<W-d (bbELS centre), 2 = the complement. */
 int cds_finalize(const float* x, const float* beta, const float* m, const float* l, const float* acc,
