@@ -298,8 +298,12 @@ def run_ours(args, scales):
         }
         print(json.dumps(out))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # no collective after the timed region: tearing down a NCCL communicator that is referenced by captured CUDA
+        # graphs can block, so every rank just drains its own stream and leaves
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
