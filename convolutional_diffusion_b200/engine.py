@@ -74,10 +74,20 @@ class ScoreEngine:
         planes = 1 if b.strip8()[1] is None else 2
         return self.lib.cds_els_umma_smem_bytes(b.C, b.H, b.W, k, passes, planes) > 0
 
-    def _splits(self, tiles, B, n_sel, waves=1):
-        ctas = max(1, tiles * B)
-        s = max(1, (sm_count(self.device) * waves) // ctas)
-        return int(min(s, n_sel))
+    def _splits(self, tiles, B, n_sel, waves=4, min_images=16):
+        """Bank slices per (query tile, sample) so that the grid fills whole waves of SMs: picks the split count
+        with the best wave efficiency ctas / (ceil(ctas/SMs)*SMs) among up to `waves` full waves, preferring fewer CTAs
+        on ties, and never leaves a CTA with fewer than min_images images (fixed per-CTA setup cost)."""
+        sms = sm_count(self.device)
+        base = max(1, tiles * B)
+        best, best_eff = 1, 0.0
+        smax = max(1, min(n_sel // max(1, min_images), (sms * waves) // base))
+        for s in range(1, smax + 1):
+            ctas = base * s
+            eff = ctas / (((ctas + sms - 1) // sms) * sms)
+            if eff > best_eff + 0.03:
+                best, best_eff = s, eff
+        return int(max(1, min(best, n_sel)))
 
     # ---- kernels -------------------------------------------------------------------------------
     def simt_partials(self, kind, pad, x, beta, k, sel, region=0, tag="simt"):
@@ -85,7 +95,7 @@ class ScoreEngine:
         b = self.bank
         B = x.shape[0]
         tiles = (b.H * b.W + 127) // 128
-        S = self._splits(tiles, B, n_sel, waves=4)
+        S = self._splits(tiles, B, n_sel, waves=4, min_images=8)
         P = self._partials(tag, S, B)
         _lib.check(self.lib.cds_partials_simt(_lib.KIND[kind], _lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k,
                                               _lib.ptr(beta), _lib.ptr(b.images), _lib.ptr(idx), _lib.ptr(logw),
