@@ -212,8 +212,10 @@ __global__ void finalize_kernel(const float* __restrict__ x, const float* __rest
   if (g >= B * HW) return;
   const int b = g / HW, pix = g % HW, i = pix / W, j = pix % W;
   if (region != 0) {
-    const bool centre = i >= d && i < H - d && j >= d && j < W - d;
-    if ((region == 1) != centre) return;
+    const bool rb = i < d || i >= H - d, cb = j < d || j >= W - d;
+    const bool centre = !rb && !cb, corner = rb && cb;
+    const bool in = region == 1 ? centre : region == 2 ? !centre : region == 3 ? corner : (!centre && !corner);
+    if (!in) return;
   }
   const float bt = beta[b], a = sqrtf(1.f - bt);
   const float inv = 1.f / l[(size_t)b * HW + pix];

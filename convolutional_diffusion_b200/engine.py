@@ -123,6 +123,23 @@ class ScoreEngine:
         self.launches += 1
         return P
 
+    def edge_supported(self, k):
+        b = self.bank
+        return self.use_tensor_cores and bool(self.lib.cds_bbels_edge_supported(b.C, b.H, b.W, k))
+
+    def edge_partials(self, x, beta, k, sel, tag="edge"):
+        """bbELS edge bands (csrc/bbels_edge.cu); writes the edge pixels of the partials only."""
+        idx, logw, n_sel = sel
+        b = self.bank
+        B = x.shape[0]
+        S = int(max(1, min(n_sel // 8, (4 * sm_count(self.device)) // (4 * B))))
+        P = self._partials(tag, S, B)
+        _lib.check(self.lib.cds_bbels_edge_partials(_lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(b.images),
+                                                    _lib.ptr(idx), _lib.ptr(logw), n_sel, S, _lib.ptr(P.m), _lib.ptr(P.l),
+                                                    _lib.ptr(P.acc), _lib.stream_ptr()), "cds_bbels_edge_partials")
+        self.launches += 1
+        return P
+
     def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma"):
         idx, logw, n_sel = sel
         b = self.bank
@@ -199,9 +216,16 @@ class ScoreEngine:
             d = k // 2
             if self.umma_supported(k, passes):
                 Pc = self.combine(self.umma_partials("zeros", x, beta, k, sel, passes))
-                Pb = self.combine(self.simt_partials("bbELS", "zeros", x, beta, k, sel, region=2, tag="border"))
                 self.finalize(Pc, x, beta, mu, score, region=1, d=d)
-                self.finalize(Pb, x, beta, mu, score, region=2, d=d)
+                if self.edge_supported(k) and self.ls_supported(k):
+                    # edge bands: dedicated kernel; corners see only their own location = the LS kernel
+                    Pe = self.combine(self.edge_partials(x, beta, k, sel))
+                    self.finalize(Pe, x, beta, mu, score, region=4, d=d)
+                    Pk = self.combine(self.ls_partials(x, beta, k, sel, tag="corner"))
+                    self.finalize(Pk, x, beta, mu, score, region=3, d=d)
+                else:
+                    Pb = self.combine(self.simt_partials("bbELS", "zeros", x, beta, k, sel, region=2, tag="border"))
+                    self.finalize(Pb, x, beta, mu, score, region=2, d=d)
             else:
                 P = self.combine(self.simt_partials("bbELS", "zeros", x, beta, k, sel))
                 self.finalize(P, x, beta, mu, score)

@@ -74,6 +74,14 @@ int cds_ls_partials(const float* x, int B, int C, int H, int W, int k, const flo
                     const int32_t* idx, const float* logw, int64_t n_sel, int splits, float* m, float* l, float* acc,
                     void* stream);
 
+/* bbELS edge bands (idealscore.py:256-288): queries whose patch crosses exactly one border vs the zero-padded
+ * patches at the same depth and every interior position along the band.  Exact fp32; square images, odd k <= 31.
+ * Writes the partials of the edge pixels only. */
+int cds_bbels_edge_supported(int C, int H, int W, int k);
+int cds_bbels_edge_partials(const float* x, int B, int C, int H, int W, int k, const float* beta, const float* images,
+                            const int32_t* idx, const float* logw, int64_t n_sel, int splits, float* m, float* l,
+                            float* acc, void* stream);
+
 /* tcgen05 / TMEM evaluation of ELS (and the bbELS centre region): queries = all H*W pixels of x padded
  * per query_pad, candidates = every valid k x k patch of the selected images, streamed from the strip8
  * bank by bulk-async copies.  passes = 1: fp16 query; 2: fp16 hi+lo query (fp32-grade dot products for
@@ -99,7 +107,8 @@ int cds_combine_packed(const float* packed, int S, int B, int C, int HW, float* 
                        void* stream);
 
 /* mu = acc/l ; score = -(x - sqrt(1-beta) mu)/beta  (idealscore.py:372,473,557).
- * region: 0 = all pixels, 1 = only pixels with d<=i<H-d and d<=j<W-d (bbELS centre), 2 = the complement. */
+ * region: 0 = all pixels, 1 = only pixels with d<=i<H-d and d<=j<W-d (bbELS centre), 2 = the complement,
+ * 3 = corners (both coordinates within d of a border), 4 = edge bands (exactly one). */
 int cds_finalize(const float* x, const float* beta, const float* m, const float* l, const float* acc,
                  int B, int C, int H, int W, int region, int d, float* mu, float* score, void* stream);
 
