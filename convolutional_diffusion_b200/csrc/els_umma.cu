@@ -33,7 +33,7 @@ namespace {
 constexpr int TI = 16, TJ = 8;           // query tile: 16 rows x 8 columns = 128 queries = UMMA M
 constexpr int MAX_STAGES = 2;
 constexpr int MAX_CHUNKS = 4;
-constexpr int NUM_EPI_WG = 4;            // epilogue warpgroups: a pair per TMEM buffer, splitting its columns
+constexpr int NUM_EPI_WG = 4;            // epilogue warpgroups: all of them consume every tile, each a quarter of its columns
 constexpr int THREADS = 128 + 128 * NUM_EPI_WG;   // 4 control warps + the epilogue warpgroups
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_MMAS = 320;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     }
     for (int q = 0; q < 2; ++q) {
       mbar_init(bar_tfull + 8 * q, 1);
-      mbar_init(bar_tempty + 8 * q, 2 * NUM_EPI_WG);      // the warps of the two warpgroups sharing this buffer
+      mbar_init(bar_tempty + 8 * q, 4 * NUM_EPI_WG);      // every epilogue warp reads every tile
     }
     fence_barrier_init();
   }
@@ -396,9 +396,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     }
   } else {
     // =========================== epilogue
-    // warpgroup wg: TMEM buffer / tile parity pr2 = wg & 1, column half hf2 = wg >> 1 (chunks hf2, hf2+2, ...)
+    // Tile T sits in TMEM buffer T & 1; while the four warpgroups drain it (warpgroup wg takes the 16-column chunks
+    // wg, wg+4, ...), the MMA warp fills the other buffer with tile T+1.
     const int wg = (warp - 4) >> 2, q = tid - 128 - wg * 128;   // q = query row = TMEM lane
-    const int pr2 = wg & 1, hf2 = wg >> 1;
     const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     const float c1 = CDS_LOG2E * a / beta * inv_scale;   // accumulator -> log2-unit logit
@@ -411,34 +411,32 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     float* dbg = (p.dbg && split == 0 && qi < g.H && qj < g.W)
                      ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
                      : nullptr;
-    long long T = 0;
+    const int nchunks = g.nchunks, nvb = g.nvb, vt_tile = g.vt_tile;
+    uint32_t T = 0;
     for (int n = 0; n < n_img; ++n) {
       const int s = n % S;
       mbar_wait(bar_vready + 8 * s, (n / S) & 1, 4);
-      const float* vt = reinterpret_cast<const float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
+      const float* vtile = reinterpret_cast<const float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
       const bool dump = (dbg != nullptr) && n == 0;
-      int tt = 0;
-      for (int ch = 0; ch < g.nchunks; ++ch) {
+      for (int ch = 0; ch < nchunks; ++ch) {
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
-        for (int vb = 0; vb < g.nvb; ++vb, ++T, ++tt) {
-          if ((int)(T & 1) != pr2) continue;
-          const int buf = pr2;
-          const float* v01 = vt + (size_t)tt * g.vt_tile;
-          const float* v2 = v01 + 2 * N;
-          mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
+        for (int vb = 0; vb < nvb; ++vb, ++T, vtile += vt_tile) {
+          const uint32_t buf = T & 1u;
+          const float* v01 = vtile;
+          const float* v2 = vtile + 2 * N;
+          mbar_wait(bar_tfull + 8 * buf, (T >> 1) & 1u, 5);
           tc_fence_after();
           const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
-          const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
           // partial blocks inside the row and rounded-up patch rows are already masked by the norm plane's marker;
           // explicit masking is only needed when an 8-column block runs past the end of the image row
           const bool edge = 8 * vb + 8 > g.W;
-          for (int c0 = 16 * hf2; c0 < N; c0 += 32) {
+          const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
+          for (int c0 = 16 * wg; c0 < N; c0 += 16 * NUM_EPI_WG) {
             uint32_t r[16];
             tmem_ld16(taddr + c0, r);
             tmem_ld_wait16(r);
-            // columns that are not valid patches (partial last 8-column block, rounded-up last patch row) are
-            // forced to -FLT_MAX: they never win the max and get weight 0.  Warp-uniform, only in edge tiles.
+            // columns that are not valid patches are forced to -FLT_MAX: they never win the max and get weight 0
             if (edge) {
 #pragma unroll
               for (int e = 0; e < 16; ++e)
@@ -471,19 +469,20 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             // pass 2: weights and weighted sums
             const float off = lw - m;
             const float2 off2 = make_float2(off, off);
+            const float* pv01 = v01 + 2 * c0;
+            const float* pv2 = v2 + c0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float2 ar = fma2(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), c1c1, off2);
               const float2 w = make_float2(ex2(ar.x), ex2(ar.y));
               l2 = add2(l2, w);
-              const int pr = (c0 >> 1) + e;
               if (C == 1) {
-                acc2[0] = fma2(w, *reinterpret_cast<const float2*>(v01 + 4 * pr), acc2[0]);
+                acc2[0] = fma2(w, *reinterpret_cast<const float2*>(pv01 + 4 * e), acc2[0]);
               } else {
-                const float4 vv = *reinterpret_cast<const float4*>(v01 + 4 * pr);
+                const float4 vv = *reinterpret_cast<const float4*>(pv01 + 4 * e);
                 acc2[0] = fma2(w, make_float2(vv.x, vv.y), acc2[0]);
                 acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
-                if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(v2 + 2 * pr), acc2[2 % C]);
+                if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(pv2 + 2 * e), acc2[2 % C]);
               }
             }
           }
