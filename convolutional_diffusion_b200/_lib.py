@@ -33,6 +33,9 @@ SIGNATURES = {
     "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,
                                    _p, _p, _p, _p, _p]),
     "cds_els_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "cds_els_partials_umma_pv": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,
+                                      _p, _p, _p, _p, _p]),
+    "cds_els_umma_pv_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
     "cds_combine": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "cds_combine_packed": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "cds_finalize": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

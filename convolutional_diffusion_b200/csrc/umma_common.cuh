@@ -1,0 +1,279 @@
+// Shared pieces of the tcgen05 ELS kernels: geometry, launch parameters, PTX wrappers, descriptor-table builder.
+#pragma once
+#include "common.cuh"
+#include "../../include/cdscore.h"
+
+namespace umma {
+
+
+constexpr int TI = 16, TJ = 8;           // query tile: 16 rows x 8 columns = 128 queries = UMMA M
+constexpr int MAX_STAGES = 2;
+constexpr int MAX_CHUNKS = 4;
+constexpr int NUM_EPI_WG = 4;            // epilogue warpgroups: all of them consume every tile, each a quarter of its columns
+constexpr int THREADS = 128 + 128 * NUM_EPI_WG;   // 4 control warps + the epilogue warpgroups
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_MMAS = 320;
+constexpr float SKIP_LOG2 = 40.f;        // chunks whose weights are all < 2^-40 of the running max are skipped
+constexpr float INVALID_NORM = 60000.f;  // norm-plane marker of positions that are not valid patches
+
+struct UmmaGeom {
+  int C, H, W, k, d, Ph, Pw;
+  int nb;             // dy blocks of 8 rows
+  int RA;             // bytes between query rows in the A tile = (k+7)*16
+  int a_block;        // bytes of one (c,b) block of A = TI*RA
+  int a_plane;        // bytes of one precision plane of A = C*nb*a_block
+  int a_const;        // byte offset of the constant (-a*scale/2) block in A
+  int a_zero;         // byte offset of the zero block in A
+  int a_bytes;
+  int S1;             // bytes of one image row of granules = W*16
+  int img_bytes;      // C*H*W*16
+  int np_bytes;       // H*W*16 (norm plane of one image)
+  int tile_pad;       // zeroed guard after each staged tile
+  int np_off;         // offset of the norm plane inside a stage
+  int vt_off;         // offset of the centre-pixel table inside a stage
+  int vt_tile;        // floats per tile of that table: [N/2 pairs][4] (v0,v1) + [N/2][2] (v2); PV variant: the
+                      // fp16 UMMA operand V'^T [16 rows][N] K-major = N*32 bytes per tile
+  int pv;             // 1 = geometry of the P.V (weighted sum on the tensor cores) variant
+  int stage_bytes;
+  int stages;
+  int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
+  int nvb;            // 8-column blocks of candidate patches
+  int n_mma;          // descriptor-table entries per accumulator tile (all precision combinations)
+  int passes, bank_planes;
+  int smem_A, smem_stage, smem_merge, smem_table, smem_bar, smem_total;
+};
+
+struct UmmaParams {
+  UmmaGeom g;
+  int B, pad, splits;
+  long long n_sel;
+  const float* x;
+  const float* beta;
+  const uint8_t* bank_hi;
+  const uint8_t* bank_lo;
+  const uint8_t* norm_plane;
+  float scale;
+  const int32_t* idx;
+  const float* logw;
+  float *m, *l, *acc, *dbg;
+  uint2 table[MAX_MMAS];   // lo words of the (A,B) descriptors relative to the A base / the tile origin in a stage
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must become a trap (CUDA error), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  for (uint32_t it = 0; it < (1u << 22); ++it)
+    if (mbar_try(bar, parity)) return;
+  printf("cdscore: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// the wait names the destination registers as in/out operands so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+// packed fp32x2 arithmetic (sm_100+): two FMAs per issue slot
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// one lane of a converged warp (the warp stays converged around it, so descriptors live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.b32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major, no-swizzle shared memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4   [16,30) LBO>>4 (stride between the two K granules)   [32,46) SBO>>4 (stride between
+//   8-row groups)   [46,48) version = 1   [61,64) layout = 0 (interleave / no swizzle)
+__device__ __forceinline__ uint64_t desc_hi(uint32_t sbo_bytes) {
+  return ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+
+
+// ------------------------------------------------------------------ host side: geometry + descriptor table
+struct Gran { int a, b; };
+
+// pairs consecutive K granules of one precision combination into UMMA descriptors (K = 16 = two granules);
+// an odd tail is paired with the zero block on the query side
+inline int emit_pairs(const Gran* gr, int n, int a_zero, uint2* table, int nm) {
+  for (int q = 0; q < n; q += 2) {
+    if (nm >= MAX_MMAS) return -1;
+    int la, lb;
+    if (q + 1 < n) { la = gr[q + 1].a - gr[q].a; lb = gr[q + 1].b - gr[q].b; }
+    else           { la = a_zero - gr[q].a;      lb = 16; }
+    if (la <= 0 || lb <= 0 || (la >> 4) > 0x3FFF || (lb >> 4) > 0x3FFF) return -1;
+    table[nm].x = (uint32_t)(gr[q].a >> 4) | ((uint32_t)(la >> 4) << 16);
+    table[nm].y = (uint32_t)(gr[q].b >> 4) | ((uint32_t)(lb >> 4) << 16);
+    ++nm;
+  }
+  return nm;
+}
+
+inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom& g, uint2* table, int pv = 0) {
+  if (C < 1 || C > 3 || H > 32 || W > 32 || H < k || W < k || (k & 1) == 0 || k < 3) return 0;
+  if (passes < 1 || passes > 2 || bank_planes < 1 || bank_planes > 2) return 0;
+  g.C = C; g.H = H; g.W = W; g.k = k; g.d = k / 2;
+  g.Ph = H - k + 1; g.Pw = W - k + 1;
+  g.nb = (k + 7) / 8;
+  g.RA = (k + 7) * 16;
+  g.a_block = TI * g.RA;
+  g.a_plane = C * g.nb * g.a_block;
+  g.a_const = passes * g.a_plane;
+  g.a_zero = g.a_const + g.a_block;
+  g.a_bytes = g.a_zero + g.a_block;
+  g.S1 = W * 16;
+  g.img_bytes = C * H * W * 16;
+  g.np_bytes = H * W * 16;
+  g.tile_pad = ((k + 8) * 16 + 127) / 128 * 128;
+  g.np_off = bank_planes * (g.img_bytes + g.tile_pad);
+  g.vt_off = g.np_off + g.np_bytes + g.tile_pad;
+  g.passes = passes; g.bank_planes = bank_planes;
+  // patch-row chunks: N = 8*G <= 256, G even (UMMA M=128 needs N % 16 == 0)
+  int rows = g.Ph, u0 = 0, gmax = 0;
+  g.nchunks = 0;
+  while (rows > 0) {
+    if (g.nchunks == MAX_CHUNKS) return 0;
+    const int G = rows > 32 ? 32 : rows;
+    int Ge = (G + 1) & ~1;
+    if (Ge < 2) Ge = 2;
+    g.chunk_u0[g.nchunks] = u0; g.chunk_g[g.nchunks] = Ge;
+    if (Ge > gmax) gmax = Ge;
+    ++g.nchunks; u0 += G; rows -= G;
+  }
+  g.nvb = (g.Pw + 7) / 8;
+  // a rounded-up last patch row must stay inside the strip array: u + 8*(nb-1) <= H-1
+  if (g.chunk_u0[g.nchunks - 1] + g.chunk_g[g.nchunks - 1] - 1 + 8 * (g.nb - 1) > H - 1) return 0;
+  g.pv = pv;
+  g.vt_tile = pv ? 8 * gmax * 32 / 4 : 8 * gmax / 2 * 6;   // floats per tile (see UmmaGeom::vt_tile)
+  if (pv && 8 * gmax > 240) return 0;                // two S buffers + two O tiles must fit 512 TMEM columns
+  const int vt_bytes = g.nchunks * g.nvb * g.vt_tile * 4;
+  g.stage_bytes = (g.vt_off + vt_bytes + 127) / 128 * 128;
+
+  // K granule lists per precision combination (query plane, bank plane): (0,0)+norm granule [, (1,0)] [, (0,1)]
+  Gran gr[3 * 4 * 32 + 2];
+  int nm = 0;
+  for (int cb = 0; cb < passes + bank_planes - 1; ++cb) {
+    const int pa = (cb == 1 && passes > 1) ? 1 : 0;
+    const int pb = (cb > 0 && !pa) ? 1 : 0;
+    int n = 0;
+    for (int c = 0; c < C; ++c)
+      for (int blk = 0; blk < g.nb; ++blk)
+        for (int dx = 0; dx < k; ++dx) {
+          gr[n].a = pa * g.a_plane + (c * g.nb + blk) * g.a_block + dx * 16;
+          gr[n].b = pb * (g.img_bytes + g.tile_pad) + (c * H + 8 * blk) * g.S1 + dx * 16;
+          ++n;
+        }
+    if (cb == 0) { gr[n].a = g.a_const; gr[n].b = g.np_off; ++n; }
+    nm = emit_pairs(gr, n, g.a_zero, table, nm);
+    if (nm < 0) return 0;
+  }
+  g.n_mma = nm;
+  g.smem_A = (g.a_bytes + 1023) / 1024 * 1024;
+  g.smem_merge = ((NUM_EPI_WG - 1) * 128 * 5 * 4 + 127) / 128 * 128;
+  g.smem_table = (nm * 8 + 127) / 128 * 128;
+  g.smem_bar = 8 * 10 + 16 + 32;
+  const int fixed = g.smem_A + g.smem_merge + g.smem_table + g.smem_bar + 1024;
+  g.stages = MAX_STAGES;
+  while (g.stages > 1 && fixed + g.stages * g.stage_bytes > 227 * 1024) --g.stages;
+  g.smem_stage = g.stages * g.stage_bytes;
+  g.smem_total = fixed + g.smem_stage;
+  if (g.smem_total > 227 * 1024) return 0;
+  if (pv && g.stages < 2) return 0;                  // the P.V pipeline releases a stage two tiles late
+  return 1;
+}
+
+
+}  // namespace umma

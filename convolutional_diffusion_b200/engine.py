@@ -45,6 +45,7 @@ class ScoreEngine:
         self.precision = precision
         self.use_tensor_cores = use_tensor_cores
         self.group = group                       # torch.distributed process group for bank sharding (or None)
+        self.els_variant = "pv"                  # "pv": weighted sum on the tensor cores when the geometry allows; "v2
         self._buf = {}
         self.launches = 0                        # kernels launched through this engine (bench bookkeeping)
 
@@ -58,14 +59,14 @@ class ScoreEngine:
     def passes_for(self, k, beta_min):
         """Tensor-core passes over the query: 1 = fp16 query (11-bit significand), 2 = fp16 hi + lo residual
         (22 bits, fp32-grade).  "auto" uses one pass while the logit gain a/beta that multiplies the dot-product
-        rounding error is <= 1: measured on the headline workload (profiles/r01_precision_probe.log) the
+        rounding error is <= 1.25: measured on the headline workload (profiles/r01_precision_probe.log) the
         denoised estimate then moves by < 2e-4 max-abs, 5x inside the 1e-3 tolerance."""
         if self.precision == "f16":
             return 1
         if self.precision == "f16x2":
             return 2
         a_over_b = (max(1.0 - beta_min, 0.0) ** 0.5) / max(beta_min, 1e-6)
-        return 1 if a_over_b <= 1.0 else 2
+        return 1 if a_over_b <= 1.25 else 2
 
     def umma_supported(self, k, passes):
         b = self.bank
@@ -149,7 +150,11 @@ class ScoreEngine:
         tiles = ((b.H + 15) // 16) * ((b.W + 7) // 8)
         S = self._splits(tiles, B, n_sel)
         P = self._partials(tag, S, B)
-        _lib.check(self.lib.cds_els_partials_umma(_lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta),
+        planes = 1 if lo is None else 2
+        fn = self.lib.cds_els_partials_umma
+        if self.els_variant == "pv" and self.lib.cds_els_umma_pv_smem_bytes(b.C, b.H, b.W, k, passes, planes) > 0:
+            fn = self.lib.cds_els_partials_umma_pv
+        _lib.check(fn(_lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta),
                                                   _lib.ptr(hi), _lib.ptr(lo), scale, _lib.ptr(pn), _lib.ptr(idx),
                                                   _lib.ptr(logw), n_sel, S, passes, _lib.ptr(P.m), _lib.ptr(P.l),
                                                   _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr()),

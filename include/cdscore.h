@@ -92,6 +92,15 @@ int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, in
                           const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
                           int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
                           void* stream);
+/* Same contract, "P.V" variant: the weighted sum of the centre pixels also runs on the tensor cores (P is written
+ * back to TMEM as fp16 and contracted with the per-tile value operand by a second UMMA).  Needs N <= 240 candidates
+ * per accumulator tile and two shared-memory stages; cds_els_umma_pv_smem_bytes() == 0 means use the variant above. */
+int cds_els_partials_umma_pv(int query_pad, const float* x, int B, int C, int H, int W, int k,
+                             const float* beta, const void* bank_hi, const void* bank_lo, float bank_scale,
+                             const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
+                             int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
+                             void* stream);
+int64_t cds_els_umma_pv_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes);
 /* dynamic shared memory the umma kernel needs for this geometry (0 = unsupported geometry) */
 int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes);
 

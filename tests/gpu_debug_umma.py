@@ -30,6 +30,7 @@ def main():
         imgs, labels = synthetic_bank(6, C, H, seed=1)
         bank = PatchBank(imgs, labels, device="cuda")
         eng = ScoreEngine(bank, precision="f16x2" if passes == 2 else "f16")
+        eng.els_variant = os.environ.get("CDS_VARIANT", "pv")
         ok = eng.umma_supported(k, passes)
         print(f"C={C} H={H} k={k} passes={passes} pad={pad} supported={ok}", flush=True)
         if not ok:

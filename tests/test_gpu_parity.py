@@ -111,8 +111,12 @@ def _oracle_mu(kind, x, bank, labels, label, beta, k, bs, ms=None):
     ("LS", 1, 28, 512, 5, 0.40, None, 512),
     ("LS", 3, 32, 256, 7, 0.70, 4, 256),
 ])
-def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs):
-    """CIFAR / MNIST geometries at bank sizes the float64 oracle finishes in seconds."""
+@pytest.mark.parametrize("variant", ["pv", "v2"])
+def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs, variant):
+    """CIFAR / MNIST geometries at bank sizes the float64 oracle finishes in seconds; both tensor-core kernel
+    variants (weighted sum on the tensor cores / on the FMA pipe)."""
+    if variant == "v2" and kind == "LS":
+        pytest.skip("LS does not use the tensor-core kernels")
     from oracle import score_oracle as so
     from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
     bank, labels = synthetic_bank(N, C, H, nlabels=5, seed=11)
@@ -120,6 +124,7 @@ def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs):
     B = 2
     x = noisy_query(bank, beta, B, seed=5)
     mod = _make(kind, (bank, labels), k, bs, None)
+    mod.engine("cuda").els_variant = variant
     lab = None if label is None else torch.tensor([label])
     s = mod(torch.full((B,), t), x.cuda(), label=lab, device=torch.device("cuda")).cpu().double().numpy()
     for b in range(B):                                 # B samples == B independent b=1 reference calls
