@@ -198,14 +198,17 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
     int T = 0;
     for (int n = 0; n < n_img; ++n) {
       const int s = n % S;
-      mbar_wait(bar_full + 8 * s, (n / S) & 1, 2);
-      tc_fence_after();
       const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
       for (int ch = 0; ch < g.nchunks; ++ch) {
         const uint32_t N = 8u * g.chunk_g[ch];
         const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
         for (int vb = 0; vb < g.nvb; ++vb, ++T) {
+          // the pending P.V first: it may be the commit that releases the stage the next image is waiting for
           if (T >= 2) issue_pv(T - 2);
+          if (ch == 0 && vb == 0) {
+            mbar_wait(bar_full + 8 * s, (n / S) & 1, 2);
+            tc_fence_after();
+          }
           const int buf = T & 1;
           const uint32_t d_tmem = tmem_base + buf * S_BUF_COLS;
           const uint32_t b_base = (stage_addr + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
