@@ -259,10 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           // explicit masking is only needed when an 8-column block runs past the end of the image row
           const bool edge = 8 * vb + 8 > g.W;
           const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
-          for (int c0 = 16 * wg; c0 < N; c0 += 16 * NUM_EPI_WG) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait16(r);
+          auto chunk = [&](uint32_t* r, int c0) {
             // columns that are not valid patches are forced to -FLT_MAX: they never win the max and get weight 0
             if (edge) {
 #pragma unroll
@@ -284,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             }
             // every weight of this chunk is < 2^-40 of the running max for all 32 queries of the warp: adding them
             // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
-            if (__all_sync(0xffffffffu, cmax < m - SKIP_LOG2)) continue;
+            if (__all_sync(0xffffffffu, cmax < m - SKIP_LOG2)) return;
             if (cmax > m) {                        // rare after the first few images
               const float sc = ex2(m - cmax);
               const float2 sc2 = make_float2(sc, sc);
@@ -311,6 +308,23 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
                 acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
                 if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(pv2 + 2 * e), acc2[2 % C]);
               }
+            }
+          };
+          // software-pipelined TMEM reads: the next chunk's tcgen05.ld is in flight while this one is consumed
+          {
+            uint32_t ra[16], rb[16];
+            int c0 = 16 * wg;
+            if (c0 < N) tmem_ld16(taddr + c0, ra);
+            while (c0 < N) {
+              tmem_ld_wait16(ra);
+              const int c1n = c0 + 16 * NUM_EPI_WG;
+              if (c1n < N) tmem_ld16(taddr + c1n, rb);
+              chunk(ra, c0);
+              if (c1n >= N) break;
+              tmem_ld_wait16(rb);
+              c0 = c1n + 16 * NUM_EPI_WG;
+              if (c0 < N) tmem_ld16(taddr + c0, ra);
+              chunk(rb, c1n);
             }
           }
           tc_fence_before();

@@ -6,6 +6,8 @@ trajectory can be captured in one CUDA graph (machine.py).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -45,7 +47,9 @@ class ScoreEngine:
         self.precision = precision
         self.use_tensor_cores = use_tensor_cores
         self.group = group                       # torch.distributed process group for bank sharding (or None)
-        self.els_variant = "pv"                  # "pv": weighted sum on the tensor cores when the geometry allows; "v2
+        # ELS tensor-core kernel: "v2" = weighted sum on the FMA pipe (default, faster as measured in round 1),
+        # "pv" = weighted sum as a second UMMA (csrc/els_umma_pv.cu); CDS_ELS_VARIANT overrides for A/B runs
+        self.els_variant = os.environ.get("CDS_ELS_VARIANT", "v2")
         self._buf = {}
         self.launches = 0                        # kernels launched through this engine (bench bookkeeping)
 
