@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #define CDS_OK 0
 #define CDS_ERR_ARG -1

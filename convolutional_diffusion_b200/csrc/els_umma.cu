@@ -259,6 +259,12 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           // explicit masking is only needed when an 8-column block runs past the end of the image row
           const bool edge = 8 * vb + 8 > g.W;
           const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
+          if (p.flags & 2) {     // profiling: MMA pipeline only
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            continue;
+          }
           auto chunk = [&](uint32_t* r, int c0) {
             // columns that are not valid patches are forced to -FLT_MAX: they never win the max and get weight 0
             if (edge) {
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             // every weight of this chunk is < 2^-40 of the running max for all 32 queries of the warp: adding them
             // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
             if (__all_sync(0xffffffffu, cmax < m - SKIP_LOG2)) return;
+            if (p.flags & 1) { m = fmaxf(m, cmax); return; }     // profiling: pass 1 only
             if (cmax > m) {                        // rare after the first few images
               const float sc = ex2(m - cmax);
               const float2 sc2 = make_float2(sc, sc);
@@ -451,6 +458,10 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
   p.scale = bank_scale;
   p.idx = idx; p.logw = logw;
   p.m = m; p.l = l; p.acc = acc; p.dbg = dbg_dots;
+  {
+    const char* f = getenv("CDS_DEBUG_FLAGS");
+    p.flags = f ? atoi(f) : 0;
+  }
   const int tiles = ((H + TI - 1) / TI) * ((W + TJ - 1) / TJ);
   dim3 grid(tiles, splits, B);
   cudaStream_t st = (cudaStream_t)stream;

@@ -444,6 +444,7 @@ extern "C" int cds_els_partials_umma_pv(int query_pad, const float* x, int B, in
   p.scale = bank_scale;
   p.idx = idx; p.logw = logw;
   p.m = m; p.l = l; p.acc = acc; p.dbg = dbg_dots;
+  p.flags = 0;
   const int tiles = ((H + TI - 1) / TI) * ((W + TJ - 1) / TJ);
   dim3 grid(tiles, splits, B);
   cudaStream_t st = (cudaStream_t)stream;

@@ -56,6 +56,7 @@ struct UmmaParams {
   const int32_t* idx;
   const float* logw;
   float *m, *l, *acc, *dbg;
+  int flags;               // profiling switches (CDS_DEBUG_FLAGS): 1 = skip pass 2, 2 = skip the whole epilogue math
   uint2 table[MAX_MMAS];   // lo words of the (A,B) descriptors relative to the A base / the tile origin in a stage
 };
 

@@ -204,6 +204,8 @@ class ScoreEngine:
             beta_min = float(beta.min())         # host sync; the machine passes beta_min explicitly
         if kind == "bbELS" and k >= b.H:          # idealscore.py:163-164: delegate to the internal LS module
             kind, sel = "LS", (sel_ls if sel_ls is not None else sel)
+        if kind == "IS":                          # whole-image window: the LS kernel with k = 2*max(H,W)-1
+            kind, k = "LS", 2 * max(b.H, b.W) - 1
         if kind == "LS":
             if self.use_tensor_cores and self.ls_supported(k):
                 P = self.ls_partials(x, beta, k, sel)

@@ -160,5 +160,20 @@ class LocalEquivBordersScoreModule(_ScoreModuleBase):
         self.channels = channels
 
 
+class IdealScoreModule(_ScoreModuleBase):
+    """IS (idealscore.py:560-636): whole-image posterior mean.  It equals LS with a window that covers the whole
+    image from every pixel (k = 2*max(H,W) - 1), so it runs on the LS bank-streaming kernel; `k` is ignored as in the
+    reference (`forward(t, x, label=None, device=None, **kwargs)`)."""
+    kind = "IS"
+
+    def __init__(self, dataset, image_size=32, batch_size=128, schedule=cosine_noise_schedule, max_samples=None,
+                 shuffle=False, **kwargs):
+        super().__init__(dataset, None, batch_size, image_size, schedule, max_samples, shuffle, **_own(kwargs))
+
+    def forward(self, t, x, label=None, device=None, **kwargs):
+        k = 2 * max(int(x.shape[-1]), int(x.shape[-2])) - 1
+        return super().forward(t, x, label=label, device=device, k=k)
+
+
 def _own(kwargs):
     return {k: kwargs[k] for k in ("precision", "use_tensor_cores", "process_group", "bank") if k in kwargs}

@@ -27,6 +27,8 @@ def select(kind, labels, label, batch_size, max_samples, order=None):
     labels = np.asarray(labels)
     n = labels.shape[0]
     order = np.arange(n, dtype=np.int64) if order is None else np.asarray(order, dtype=np.int64)
+    if kind == "IS":                      # idealscore.py:600-614: the same bookkeeping as LS
+        kind = "LS"
     if kind not in ("LS", "ELS", "bbELS"):
         raise ValueError(f"unknown score module kind {kind!r}")
     batch_size = int(batch_size)

@@ -39,6 +39,8 @@ def _module(ref, kind, ds, k, bs, max_samples):
     if kind == "LS":
         return ref.LocalScoreModule(ds, kernel_size=k, batch_size=bs, max_samples=max_samples,
                                     schedule=ref.cosine_noise_schedule)
+    if kind == "IS":
+        return ref.IdealScoreModule(ds, batch_size=bs, max_samples=max_samples, schedule=ref.cosine_noise_schedule)
     raise ValueError(kind)
 
 
@@ -63,6 +65,9 @@ def module_cases(ref):
         ("LS", 3, 16, 48, 7, 0.80, 2, 48, None, 3),
         ("LS", 1, 28, 24, 5, 0.40, None, 24, None, 6),      # MNIST native shape (cfg-1 geometry)
         ("LS", 3, 12, 40, 3, 0.30, None, 8, None, 0),       # equal batches: order independent
+        ("IS", 3, 12, 40, 3, 0.30, None, 16, None, 0),      # whole-image ideal score (k is ignored)
+        ("IS", 1, 16, 48, 3, 0.60, 1, 12, 30, 3),           # label filter + max_samples (post-filter count)
+        ("IS", 3, 32, 24, 3, 0.85, None, 24, None, 5),
     ]
     for kind, c, h, n, k, t, label, bs, ms, seed in spec:
         bank, labels = synthetic_bank(n, c, h, nlabels=4, seed=seed)

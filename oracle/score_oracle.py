@@ -78,7 +78,7 @@ def select_bank(kind, labels, label, batch_size, max_samples, order=None):
             if len(b) == 0:
                 continue
             w = -math.log(len(b))
-        elif kind == "LS":
+        elif kind in ("LS", "IS"):
             if label is not None:
                 b = b[labels[b] == label]
             if len(b) == 0:
@@ -237,6 +237,16 @@ def ls_mu(x, bank, beta, k, logw=None):
     return (p[:, None] * bank).sum(0) / p.sum(0)[None]
 
 
+def is_mu(x, bank, beta, logw=None):
+    """IS (idealscore.py:560-636): whole-image posterior mean, softmax over images of -||x - a T_n||^2 / (2 beta).
+    Identical to LS with a window that covers the whole image from every pixel (k >= 2H-1)."""
+    x, bank, beta, a, logw = _prep(x, bank, beta, logw)
+    dist = ((x[None] - a * bank) ** 2).sum(axis=(1, 2, 3))
+    logits = -dist / (2.0 * beta) + logw
+    p = np.exp(logits - logits.max())
+    return np.tensordot(p, bank, axes=1) / p.sum()
+
+
 def score_from_mu(x, mu, beta):
     """score = -(x - a mu)/beta  (idealscore.py:372,473,557)."""
     beta = float(beta)
@@ -252,6 +262,8 @@ def score(kind, x, bank, beta, k, logw=None):
         mu = ls_mu(x, bank, beta, k, logw) if k >= h else bbels_mu(x, bank, beta, k, logw)
     elif kind == "LS":
         mu = ls_mu(x, bank, beta, k, logw)
+    elif kind == "IS":
+        mu = is_mu(x, bank, beta, logw)
     else:
         raise ValueError(kind)
     return score_from_mu(x, mu, beta), mu

@@ -119,6 +119,13 @@ def mu(kind, x, bank, beta, k, logw=None, query_pad=None):
         return els_mu(x, bank, beta, k, logw, query_pad=query_pad or "circular")
     if kind == "LS" or (kind == "bbELS" and k >= h):
         return ls_mu(x, bank, beta, k, logw)
+    if kind == "IS":                                   # idealscore.py:560-636
+        a = math.sqrt(1.0 - beta)
+        logits = -((x[None] - a * bank) ** 2).sum(dim=(1, 2, 3)) / (2 * beta)
+        if logw is not None:
+            logits = logits + logw
+        p = torch.softmax(logits, dim=0)
+        return (p[:, None, None, None] * bank).sum(0)
     if kind == "bbELS":
         return bbels_mu(x, bank, beta, k, logw)
     raise ValueError(kind)

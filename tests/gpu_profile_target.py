@@ -11,7 +11,8 @@ from convolutional_diffusion_b200.synthetic import synthetic_bank  # noqa: E402
 
 
 def main():
-    ks = [int(a) for a in sys.argv[1:]] or [3, 17]
+    warm = "--warm" in sys.argv          # one untimed launch + the mean of 5 (not for ncu captures)
+    ks = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [3, 17]
     bank, labels = synthetic_bank(50000, 3, 32, seed=0)
     mod = LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=64, schedule=cosine_noise_schedule,
                                 precision="auto")
@@ -24,14 +25,20 @@ def main():
         beta_val = float(cosine_noise_schedule(torch.tensor([t])))
         beta = torch.full((4,), beta_val, device="cuda")
         passes = eng.passes_for(k, beta_val)
-        eng.bank.patch_norms(k)
+        eng.bank.norm_plane(k)
+        eng.bank.strip8()
+        reps = 1
+        if warm:
+            eng.umma_partials("circular", x, beta, k, sel, passes)
+            reps = 5
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng.umma_partials("circular", x, beta, k, sel, passes)
+        for _ in range(reps):
+            eng.umma_partials("circular", x, beta, k, sel, passes)
         b.record()
         torch.cuda.synchronize()
-        print(f"k={k} passes={passes} n_sel={sel[2]} {a.elapsed_time(b):.3f} ms")
+        print(f"k={k} passes={passes} n_sel={sel[2]} {a.elapsed_time(b) / reps:.3f} ms")
 
 
 if __name__ == "__main__":

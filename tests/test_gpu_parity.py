@@ -28,6 +28,8 @@ def _dataset(bank, labels):
 
 def _make(kind, ds, k, bs, ms, **kw):
     cd = _mods()
+    if kind == "IS":
+        return cd.IdealScoreModule(ds, batch_size=bs, max_samples=ms, schedule=cd.cosine_noise_schedule, **kw)
     cls = {"ELS": cd.LocalEquivScoreModule, "bbELS": cd.LocalEquivBordersScoreModule, "LS": cd.LocalScoreModule}[kind]
     return cls(ds, kernel_size=k, batch_size=bs, max_samples=ms, schedule=cd.cosine_noise_schedule, **kw)
 
@@ -258,3 +260,22 @@ def test_cifar_schedule_every_step(precision):
     psnr = 10 * np.log10(4.0 / max(float(np.mean((got - ref) ** 2)), 1e-30))
     assert psnr >= 50.0, psnr
     print(f"precision={precision}: worst per-step mu error {worst:.2e}, final PSNR {psnr:.1f} dB")
+
+
+def test_els_script_layout_and_resume(tmp_path):
+    """Drop-in driver: per-sample files results/<exp>/{seeds,els_outputs,labels}/NNNN.pt, resume, --fill."""
+    from convolutional_diffusion_b200 import els_script
+    common = ["--dataset", "cifar10", "--banksize", "200", "--scoremoduletype", "ELS", "--conditional",
+              "--results", str(tmp_path), "--expname", "t"]
+    els_script.main(common + ["--numiters", "2"])
+    d = tmp_path / "t"
+    for sub in ("seeds", "els_outputs", "labels"):
+        assert sorted(os.listdir(d / sub)) == ["0000.pt", "0001.pt"]
+    out0 = torch.load(d / "els_outputs" / "0000.pt")
+    assert out0.shape == (1, 3, 32, 32) and out0.dtype == torch.float32
+    assert torch.load(d / "labels" / "0000.pt").shape == (1,)
+    els_script.main(common + ["--numiters", "3"])                       # resumes at index 2, keeps 0 and 1
+    assert torch.equal(torch.load(d / "els_outputs" / "0000.pt"), out0)
+    assert len(os.listdir(d / "seeds")) == 3
+    els_script.main(common + ["--fill", "--idealname", "ideal", "--scoremoduletype", "IS"])   # same seeds, IS outputs
+    assert sorted(os.listdir(d / "ideal")) == ["0000.pt", "0001.pt", "0002.pt"]
