@@ -279,3 +279,22 @@ def test_els_script_layout_and_resume(tmp_path):
     assert len(os.listdir(d / "seeds")) == 3
     els_script.main(common + ["--fill", "--idealname", "ideal", "--scoremoduletype", "IS"])   # same seeds, IS outputs
     assert sorted(os.listdir(d / "ideal")) == ["0000.pt", "0001.pt", "0002.pt"]
+
+
+def test_calibration_recovers_the_kernel_size_of_an_analytic_model():
+    """scales_calibration.calibrate with a stand-in 'trained model' that IS an ELS machine of kernel size 7: the
+    calibration must pick 7 at every step (cosine similarity 1)."""
+    from convolutional_diffusion_b200.scales_calibration import calibrate
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    cd = _mods()
+    bank, labels = synthetic_bank(64, 3, 32, nlabels=4, seed=5)
+    teacher = cd.LocalEquivScoreModule((bank, labels), kernel_size=7, batch_size=8, schedule=cd.cosine_noise_schedule)
+
+    def model(t, x, label=None):
+        beta = cd.cosine_noise_schedule(t.cpu()).to(x.device)
+        return -teacher(t, x, label=label, device=x.device) * beta ** 0.5
+
+    out = calibrate(model, (bank, labels), kernelsizes=[3, 5, 7, 9], scoremoduletype="ELS", scorebatchsize=8, nsamps=2,
+                    nsteps=5, generator=torch.Generator().manual_seed(0))
+    assert out["k_optimals"].shape == (2, 5)
+    assert torch.all(out["median"] == 7) and torch.all(out["mode"] == 7)
