@@ -71,13 +71,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
-  // zero guards behind every staged tile (over-reads of masked columns must stay finite)
-  for (int s = 0; s < S; ++s)
-    for (int pl = 0; pl <= g.bank_planes; ++pl) {
-      uint8_t* pad = sStage + (size_t)s * g.stage_bytes +
-                     (pl < g.bank_planes ? (size_t)pl * (g.img_bytes + g.tile_pad) + g.img_bytes : (size_t)g.np_off + g.np_bytes);
-      for (int e = tid * 16; e < g.tile_pad; e += THREADS * 16) *reinterpret_cast<uint4*>(pad + e) = make_uint4(0, 0, 0, 0);
-    }
+  // zero the staging area once: guard pads behind the tiles and band rows past the image bottom are never written by
+  // the bulk copies, and whatever masked columns / zero-weighted K slots read there must stay finite
+  for (int e = tid * 16; e < g.smem_stage; e += THREADS * 16) *reinterpret_cast<uint4*>(sStage + e) = make_uint4(0, 0, 0, 0);
   {
     // A[plane][c][blk][gi][jj][8]: element e of granule (gi,jj) of block blk = xpad[i0+gi+8*blk+e][j0+jj] (patch
     // coordinates: padded row = pixel row + dy, i.e. source pixel row i0+gi+dy-d), zero where dy = 8*blk+e >= k
@@ -126,19 +122,27 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   const uint32_t tmem_base = *sTmemBase;
 
   if (warp == 0) {
-    // =========================== producer: bulk copies of one image (+ residual plane) and its norm plane
+    // =========================== producer: per (image, band) unit one bulk copy per channel (+ residual plane) of the
+    // band's strip rows, and one of its norm-plane rows
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(g.bank_planes * g.img_bytes + g.np_bytes);
+      int unit = 0;
       for (int n = 0; n < n_img; ++n) {
-        const int s = n % S;
-        mbar_wait(bar_empty + 8 * s, ((n / S) & 1) ^ 1, 1);
         const long long gi = p.idx[n0 + n];
-        const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
-        mbar_expect_tx(bar_full + 8 * s, tx);
-        bulk_g2s(dst, p.bank_hi + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
-        if (g.bank_planes > 1)
-          bulk_g2s(dst + g.img_bytes + g.tile_pad, p.bank_lo + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
-        bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.np_bytes, g.np_bytes, bar_full + 8 * s);
+        for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+          const int s = unit % S, u0 = g.chunk_u0[ch];
+          const uint32_t rows = (uint32_t)min(g.R, g.H - u0), nrows = (uint32_t)min(g.G, g.H - u0);
+          const uint32_t cbytes = rows * g.S1, nbytes = nrows * g.S1;
+          mbar_wait(bar_empty + 8 * s, ((unit / S) & 1) ^ 1, 1);
+          const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
+          mbar_expect_tx(bar_full + 8 * s, g.bank_planes * g.C * cbytes + nbytes);
+          for (int c = 0; c < g.C; ++c) {
+            const size_t src = ((size_t)gi * g.C + c) * g.chan_bytes + (size_t)u0 * g.S1;
+            bulk_g2s(dst + c * g.R * g.S1, p.bank_hi + src, cbytes, bar_full + 8 * s);
+            if (g.bank_planes > 1)
+              bulk_g2s(dst + g.img_bytes + g.tile_pad + c * g.R * g.S1, p.bank_lo + src, cbytes, bar_full + 8 * s);
+          }
+          bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.chan_bytes + (size_t)u0 * g.S1, nbytes, bar_full + 8 * s);
+        }
       }
     }
   } else if (warp == 1) {
@@ -149,12 +153,13 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     const uint32_t a_base = smem_u32(sA) >> 4;
     const int nm = g.n_mma;
     long long T = 0;
+    int unit = 0;
     for (int n = 0; n < n_img; ++n) {
-      const int s = n % S;
-      mbar_wait(bar_full + 8 * s, (n / S) & 1, 2);
-      tc_fence_after();
-      const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
-      for (int ch = 0; ch < g.nchunks; ++ch) {
+      for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+        const int s = unit % S;
+        mbar_wait(bar_full + 8 * s, (unit / S) & 1, 2);
+        tc_fence_after();
+        const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
         const uint32_t N = 8u * g.chunk_g[ch];
         // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
         // N>>3 at [17,23), M>>4 at [24,29)
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((T >> 1) & 1) ^ 1), 3);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * 256;
-          const uint32_t b_base = (stage_addr + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
+          const uint32_t b_base = (stage_addr + vb * 128u) >> 4;      // band-relative: patch row u0 is strip row 0
           if (elect_one()) {
             {
               const uint2 e = p.table[0];
@@ -179,24 +184,24 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           }
           __syncwarp();
         }
+        if (elect_one()) umma_commit(bar_empty + 8 * s);
+        __syncwarp();
       }
-      if (elect_one()) umma_commit(bar_empty + 8 * s);
-      __syncwarp();
     }
   } else if (warp == 2 || warp == 3) {
     // =========================== builders: centre pixels of every candidate of the staged image, in tile order:
     // tile (ch,vb), column r = 8*gr + rr <-> patch (u0+gr, 8*vb+rr); pairs of columns are stored side by side
     const int bt = tid - 64;   // 0..63
+    int unit = 0;
     for (int n = 0; n < n_img; ++n) {
-      const int s = n % S;
-      mbar_wait(bar_full + 8 * s, (n / S) & 1, 6);
-      const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
-      float* vt = reinterpret_cast<float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
-      int tt = 0;
-      for (int ch = 0; ch < g.nchunks; ++ch) {
+      for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+        const int s = unit % S;
+        mbar_wait(bar_full + 8 * s, (unit / S) & 1, 6);
+        const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
+        float* vt = reinterpret_cast<float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
-        for (int vb = 0; vb < g.nvb; ++vb, ++tt) {
-          float* v01 = vt + (size_t)tt * g.vt_tile;
+        for (int vb = 0; vb < g.nvb; ++vb) {
+          float* v01 = vt + (size_t)vb * g.vt_tile;
           float* v2 = v01 + 2 * N;
           for (int r = bt; r < N; r += 64) {
             const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             if (u < g.Ph && v < g.Pw) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
-                const size_t go = ((size_t)(c * g.H + u + g.d) * g.W + (v + g.d)) * 16;
+                const size_t go = ((size_t)(c * g.R + (u - u0) + g.d) * g.W + (v + g.d)) * 16;   // band-relative row
                 float t = __half2float(*reinterpret_cast<const __half*>(st + go));
                 if (g.bank_planes > 1)
                   t += __half2float(*reinterpret_cast<const __half*>(st + g.img_bytes + g.tile_pad + go));
@@ -217,9 +222,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             v2[2 * pr + hf] = vals[2];
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_vready + 8 * s);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_vready + 8 * s);
     }
   } else {
     // =========================== epilogue
@@ -240,13 +245,14 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
                      : nullptr;
     const int nchunks = g.nchunks, nvb = g.nvb, vt_tile = g.vt_tile;
     uint32_t T = 0;
+    int unit = 0;
     for (int n = 0; n < n_img; ++n) {
-      const int s = n % S;
-      mbar_wait(bar_vready + 8 * s, (n / S) & 1, 4);
-      const float* vtile = reinterpret_cast<const float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
       const bool dump = (dbg != nullptr) && n == 0;
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = 0; ch < nchunks; ++ch, ++unit) {
+        const int s = unit % S;
+        mbar_wait(bar_vready + 8 * s, (unit / S) & 1, 4);
+        const float* vtile = reinterpret_cast<const float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
         for (int vb = 0; vb < nvb; ++vb, ++T, vtile += vt_tile) {
           const uint32_t buf = T & 1u;
@@ -338,9 +344,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     }
     float l = l2.x + l2.y, acc[C];
 #pragma unroll

@@ -91,12 +91,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
-  for (int s = 0; s < S; ++s)
-    for (int pl = 0; pl <= g.bank_planes; ++pl) {
-      uint8_t* pad = sStage + (size_t)s * g.stage_bytes +
-                     (pl < g.bank_planes ? (size_t)pl * (g.img_bytes + g.tile_pad) + g.img_bytes : (size_t)g.np_off + g.np_bytes);
-      for (int e = tid * 16; e < g.tile_pad; e += THREADS * 16) *reinterpret_cast<uint4*>(pad + e) = make_uint4(0, 0, 0, 0);
-    }
+  for (int e = tid * 16; e < g.smem_stage; e += THREADS * 16) *reinterpret_cast<uint4*>(sStage + e) = make_uint4(0, 0, 0, 0);
   {
     // query tile (A operand), constant block and zero block: identical to els_umma.cu
     const int JW = g.k + 7;
@@ -142,19 +137,23 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
   const uint32_t tmem_base = *sTmemBase;
 
   if (warp == 0) {
-    // =========================== producer
+    // =========================== producer (one band per image in this variant: unit == image)
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(g.bank_planes * g.img_bytes + g.np_bytes);
+      const uint32_t rows = (uint32_t)min(g.R, g.H), nrows = (uint32_t)min(g.G, g.H);
+      const uint32_t cbytes = rows * g.S1, nbytes = nrows * g.S1;
       for (int n = 0; n < n_img; ++n) {
         const int s = n % S;
         mbar_wait(bar_empty + 8 * s, ((n / S) & 1) ^ 1, 1);
         const long long gi = p.idx[n0 + n];
         const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
-        mbar_expect_tx(bar_full + 8 * s, tx);
-        bulk_g2s(dst, p.bank_hi + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
-        if (g.bank_planes > 1)
-          bulk_g2s(dst + g.img_bytes + g.tile_pad, p.bank_lo + (size_t)gi * g.img_bytes, g.img_bytes, bar_full + 8 * s);
-        bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.np_bytes, g.np_bytes, bar_full + 8 * s);
+        mbar_expect_tx(bar_full + 8 * s, g.bank_planes * g.C * cbytes + nbytes);
+        for (int c = 0; c < g.C; ++c) {
+          const size_t src = ((size_t)gi * g.C + c) * g.chan_bytes;
+          bulk_g2s(dst + c * g.R * g.S1, p.bank_hi + src, cbytes, bar_full + 8 * s);
+          if (g.bank_planes > 1)
+            bulk_g2s(dst + g.img_bytes + g.tile_pad + c * g.R * g.S1, p.bank_lo + src, cbytes, bar_full + 8 * s);
+        }
+        bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.chan_bytes, nbytes, bar_full + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
           }
           const int buf = T & 1;
           const uint32_t d_tmem = tmem_base + buf * S_BUF_COLS;
-          const uint32_t b_base = (stage_addr + (uint32_t)g.chunk_u0[ch] * g.S1 + vb * 128u) >> 4;
+          const uint32_t b_base = (stage_addr + vb * 128u) >> 4;
           if (elect_one()) {
             {
               const uint2 e = p.table[0];
@@ -256,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
             if (grp == 0 && valid) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
-                const size_t go = ((size_t)(c * g.H + u + g.d) * g.W + (v + g.d)) * 16;
+                const size_t go = ((size_t)(c * g.R + (u - u0) + g.d) * g.W + (v + g.d)) * 16;
                 rows[c] = *reinterpret_cast<const __half*>(st + go);
                 if (g.bank_planes > 1) rows[C + 1 + c] = *reinterpret_cast<const __half*>(st + g.img_bytes + g.tile_pad + go);
               }

@@ -8,7 +8,7 @@ namespace umma {
 
 constexpr int TI = 16, TJ = 8;           // query tile: 16 rows x 8 columns = 128 queries = UMMA M
 constexpr int MAX_STAGES = 2;
-constexpr int MAX_CHUNKS = 4;
+constexpr int MAX_CHUNKS = 8;
 constexpr int NUM_EPI_WG = 4;            // epilogue warpgroups: all of them consume every tile, each a quarter of its columns
 constexpr int THREADS = 128 + 128 * NUM_EPI_WG;   // 4 control warps + the epilogue warpgroups
 constexpr int TMEM_COLS = 512;
@@ -26,8 +26,10 @@ struct UmmaGeom {
   int a_zero;         // byte offset of the zero block in A
   int a_bytes;
   int S1;             // bytes of one image row of granules = W*16
-  int img_bytes;      // C*H*W*16
-  int np_bytes;       // H*W*16 (norm plane of one image)
+  int G, R;           // patch rows per band (N = 8*G), strip rows staged per band and channel
+  int chan_bytes;     // H*W*16: one channel of one image (and one norm plane) in HBM
+  int img_bytes;      // C*R*W*16: one precision plane of a band in shared memory
+  int np_bytes;       // G*W*16: the band's rows of the norm plane
   int tile_pad;       // zeroed guard after each staged tile
   int np_off;         // offset of the norm plane inside a stage
   int vt_off;         // offset of the centre-pixel table inside a stage
@@ -204,7 +206,7 @@ inline int emit_pairs(const Gran* gr, int n, int a_zero, uint2* table, int nm) {
 }
 
 inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom& g, uint2* table, int pv = 0) {
-  if (C < 1 || C > 3 || H > 32 || W > 32 || H < k || W < k || (k & 1) == 0 || k < 3) return 0;
+  if (C < 1 || C > 3 || H > 64 || W > 64 || H < k || W < k || (k & 1) == 0 || k < 3) return 0;
   if (passes < 1 || passes > 2 || bank_planes < 1 || bank_planes > 2) return 0;
   g.C = C; g.H = H; g.W = W; g.k = k; g.d = k / 2;
   g.Ph = H - k + 1; g.Pw = W - k + 1;
@@ -216,32 +218,51 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.a_zero = g.a_const + g.a_block;
   g.a_bytes = g.a_zero + g.a_block;
   g.S1 = W * 16;
-  g.img_bytes = C * H * W * 16;
-  g.np_bytes = H * W * 16;
+  g.chan_bytes = H * W * 16;
   g.tile_pad = ((k + 8) * 16 + 127) / 128 * 128;
+  g.passes = passes; g.bank_planes = bank_planes;
+  g.nvb = (g.Pw + 7) / 8;
+  g.pv = pv;
+  g.smem_A = (g.a_bytes + 1023) / 1024 * 1024;
+  g.smem_merge = ((NUM_EPI_WG - 1) * 128 * 5 * 4 + 127) / 128 * 128;
+  g.smem_bar = 8 * 10 + 16 + 32;
+  const int n_gran = C * g.nb * k;
+  const int nm_max = (passes + bank_planes - 1) * ((n_gran + 2) / 2);
+  if (nm_max > MAX_MMAS) return 0;
+  g.smem_table = 128;
+  const int fixed = g.smem_A + g.smem_merge + g.smem_table + g.smem_bar + 1024;
+
+  // Staging unit = (image, band of G patch rows): the band holds the strip rows u0 .. u0+R-1 of every channel,
+  // R = G + max(8*(nb-1), d) (dy blocks of the last patch row; the centre pixels of the band's patches), plus G rows of
+  // the norm plane and the centre-pixel tables of its nvb tiles.  N = 8*G <= 256 candidates per UMMA, G even
+  // (UMMA M=128 needs N % 16 == 0).  Pick the largest G that leaves room for two stages.
+  const int halo = 8 * (g.nb - 1) > g.d ? 8 * (g.nb - 1) : g.d;
+  int bestG = 0, bestStages = 0;
+  for (int G = 32; G >= 2; G -= 2) {
+    if (G > ((g.Ph + 1) & ~1)) continue;
+    const int nch = (g.Ph + G - 1) / G;
+    if (nch > MAX_CHUNKS || nch * G > H) continue;          // norm-plane / strip rows of a partial last band must exist
+    if (pv && (nch != 1 || 8 * G > 240)) continue;          // P.V variant: one band per image, two S buffers + O tiles in TMEM
+    const int R = G + halo;
+    const int band = C * R * g.S1;
+    const int vt_tile = pv ? 8 * G * 32 / 4 : 8 * G / 2 * 6;
+    const int stage = (bank_planes * (band + g.tile_pad) + G * g.S1 + g.tile_pad + g.nvb * vt_tile * 4 + 127) / 128 * 128;
+    const int st = fixed + 2 * stage <= 227 * 1024 ? 2 : (fixed + stage <= 227 * 1024 ? 1 : 0);
+    if (st > bestStages) { bestStages = st; bestG = G; }
+    if (st == 2) break;
+  }
+  if (bestG == 0) return 0;
+  if (pv && bestStages < 2) return 0;                        // the P.V pipeline releases a stage two tiles late
+  g.G = bestG; g.R = bestG + halo;
+  g.nchunks = (g.Ph + g.G - 1) / g.G;
+  for (int c = 0; c < g.nchunks; ++c) { g.chunk_u0[c] = c * g.G; g.chunk_g[c] = g.G; }
+  g.img_bytes = C * g.R * g.S1;                              // one precision plane of a band in shared memory
+  g.np_bytes = g.G * g.S1;
   g.np_off = bank_planes * (g.img_bytes + g.tile_pad);
   g.vt_off = g.np_off + g.np_bytes + g.tile_pad;
-  g.passes = passes; g.bank_planes = bank_planes;
-  // patch-row chunks: N = 8*G <= 256, G even (UMMA M=128 needs N % 16 == 0)
-  int rows = g.Ph, u0 = 0, gmax = 0;
-  g.nchunks = 0;
-  while (rows > 0) {
-    if (g.nchunks == MAX_CHUNKS) return 0;
-    const int G = rows > 32 ? 32 : rows;
-    int Ge = (G + 1) & ~1;
-    if (Ge < 2) Ge = 2;
-    g.chunk_u0[g.nchunks] = u0; g.chunk_g[g.nchunks] = Ge;
-    if (Ge > gmax) gmax = Ge;
-    ++g.nchunks; u0 += G; rows -= G;
-  }
-  g.nvb = (g.Pw + 7) / 8;
-  // a rounded-up last patch row must stay inside the strip array: u + 8*(nb-1) <= H-1
-  if (g.chunk_u0[g.nchunks - 1] + g.chunk_g[g.nchunks - 1] - 1 + 8 * (g.nb - 1) > H - 1) return 0;
-  g.pv = pv;
-  g.vt_tile = pv ? 8 * gmax * 32 / 4 : 8 * gmax / 2 * 6;   // floats per tile (see UmmaGeom::vt_tile)
-  if (pv && 8 * gmax > 240) return 0;                // two S buffers + two O tiles must fit 512 TMEM columns
-  const int vt_bytes = g.nchunks * g.nvb * g.vt_tile * 4;
-  g.stage_bytes = (g.vt_off + vt_bytes + 127) / 128 * 128;
+  g.vt_tile = pv ? 8 * g.G * 32 / 4 : 8 * g.G / 2 * 6;      // floats per tile (see UmmaGeom::vt_tile)
+  g.stage_bytes = (g.vt_off + g.nvb * g.vt_tile * 4 + 127) / 128 * 128;
+  g.stages = bestStages;
 
   // K granule lists per precision combination (query plane, bank plane): (0,0)+norm granule [, (1,0)] [, (0,1)]
   Gran gr[3 * 4 * 32 + 2];
@@ -254,7 +275,7 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
       for (int blk = 0; blk < g.nb; ++blk)
         for (int dx = 0; dx < k; ++dx) {
           gr[n].a = pa * g.a_plane + (c * g.nb + blk) * g.a_block + dx * 16;
-          gr[n].b = pb * (g.img_bytes + g.tile_pad) + (c * H + 8 * blk) * g.S1 + dx * 16;
+          gr[n].b = pb * (g.img_bytes + g.tile_pad) + (c * g.R + 8 * blk) * g.S1 + dx * 16;   // band-relative rows
           ++n;
         }
     if (cb == 0) { gr[n].a = g.a_const; gr[n].b = g.np_off; ++n; }
@@ -262,18 +283,9 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
     if (nm < 0) return 0;
   }
   g.n_mma = nm;
-  g.smem_A = (g.a_bytes + 1023) / 1024 * 1024;
-  g.smem_merge = ((NUM_EPI_WG - 1) * 128 * 5 * 4 + 127) / 128 * 128;
-  g.smem_table = (nm * 8 + 127) / 128 * 128;
-  g.smem_bar = 8 * 10 + 16 + 32;
-  const int fixed = g.smem_A + g.smem_merge + g.smem_table + g.smem_bar + 1024;
-  g.stages = MAX_STAGES;
-  while (g.stages > 1 && fixed + g.stages * g.stage_bytes > 227 * 1024) --g.stages;
   g.smem_stage = g.stages * g.stage_bytes;
   g.smem_total = fixed + g.smem_stage;
-  if (g.smem_total > 227 * 1024) return 0;
-  if (pv && g.stages < 2) return 0;                  // the P.V pipeline releases a stage two tiles late
-  return 1;
+  return g.smem_total <= 227 * 1024;
 }
 
 

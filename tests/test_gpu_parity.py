@@ -298,3 +298,19 @@ def test_calibration_recovers_the_kernel_size_of_an_analytic_model():
                     nsteps=5, generator=torch.Generator().manual_seed(0))
     assert out["k_optimals"].shape == (2, 5)
     assert torch.all(out["median"] == 7) and torch.all(out["mode"] == 7)
+
+
+@pytest.mark.parametrize("k,t", [(3, 0.15), (9, 0.55), (17, 0.9)])
+def test_els_64x64_band_staging(k, t):
+    """64x64x3 (BASELINE config 5 geometry): the image no longer fits shared memory and is staged in row bands."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
+    bank, labels = synthetic_bank(12, 3, 64, nlabels=2, seed=31)
+    beta = float(so.cosine_beta(t))
+    x = noisy_query(bank, beta, 1, seed=7)
+    mod = _make("ELS", (bank, labels), k, 8, None)
+    assert mod.engine("cuda").umma_supported(k, 2)
+    s = mod(torch.tensor([t]), x.cuda(), device=torch.device("cuda")).cpu().double().numpy()[0]
+    mu = _mu_from_score(s, x[0].double().numpy(), beta)
+    mu_o = _oracle_mu("ELS", x[0].numpy(), bank.numpy(), labels.numpy(), None, beta, k, 8)
+    assert np.max(np.abs(mu - mu_o)) < MU_TOL

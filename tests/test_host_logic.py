@@ -92,7 +92,8 @@ def test_library_exports_every_declared_symbol():
     assert loaded.cds_abi_version() == 1
     # geometry query is host-only arithmetic: CIFAR shape, k=17, two query passes fits in 227 KB
     assert 0 < loaded.cds_els_umma_smem_bytes(3, 32, 32, 17, 2, 1) <= 227 * 1024
-    assert loaded.cds_els_umma_smem_bytes(3, 64, 64, 17, 2, 1) == 0      # not yet: falls back to the SIMT kernel
+    assert 0 < loaded.cds_els_umma_smem_bytes(3, 64, 64, 17, 1, 1) <= 227 * 1024    # 64x64: staged in row bands
+    assert loaded.cds_els_umma_smem_bytes(3, 128, 128, 5, 1, 1) == 0     # larger images fall back to the SIMT kernel
     assert loaded.cds_els_umma_smem_bytes(3, 32, 32, 4, 1, 1) == 0       # even kernel sizes are rejected
 
 
