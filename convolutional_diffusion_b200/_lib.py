@@ -28,6 +28,8 @@ SIGNATURES = {
     "cds_pack_norm_plane": (_i, [_p, _i64, _i, _i, _i, _i, _p, _p]),
     "cds_partials_simt": (_i, [_i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
     "cds_ls_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "cds_ls_rows_supported": (_i, [_i, _i, _i, _i]),
+    "cds_ls_rows_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_bbels_edge_supported": (_i, [_i, _i, _i, _i]),
     "cds_bbels_edge_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,

@@ -111,6 +111,8 @@ class ScoreEngine:
 
     def ls_supported(self, k):
         b = self.bank
+        if self.lib.cds_ls_rows_supported(b.C, b.H, b.W, k):
+            return True
         d = k // 2
         smem = (8 if b.C == 1 else 4) * 4 * (b.H * (b.W + 2 * d) + (b.H + 2 * d) * b.W)   # images per round
         return b.C in (1, 3) and b.H * b.W <= 4096 and smem <= 227 * 1024
@@ -120,9 +122,12 @@ class ScoreEngine:
         idx, logw, n_sel = sel
         b = self.bank
         B = x.shape[0]
-        S = int(min(n_sel, max(1, (2 * sm_count(self.device)) // ((B + 3) // 4))))
+        rows = bool(self.lib.cds_ls_rows_supported(b.C, b.H, b.W, k))
+        sb = 2 if rows else 4                                   # samples per CTA of the two kernels
+        S = int(min(n_sel, max(1, (2 * sm_count(self.device)) // ((B + sb - 1) // sb))))
         P = self._partials(tag, S, B)
-        _lib.check(self.lib.cds_ls_partials(_lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(b.images),
+        fn = self.lib.cds_ls_rows_partials if rows else self.lib.cds_ls_partials
+        _lib.check(fn(_lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(b.images),
                                             _lib.ptr(idx), _lib.ptr(logw), n_sel, S, _lib.ptr(P.m), _lib.ptr(P.l),
                                             _lib.ptr(P.acc), _lib.stream_ptr()), "cds_ls_partials")
         self.launches += 1

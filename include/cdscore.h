@@ -74,6 +74,14 @@ int cds_ls_partials(const float* x, int B, int C, int H, int W, int k, const flo
                     const int32_t* idx, const float* logw, int64_t n_sel, int splits, float* m, float* l, float* acc,
                     void* stream);
 
+/* The same for images up to 32 x 32 with one warp per image row: horizontal window sums by warp shuffles, one block
+ * barrier per round of 8 (C=1) / 4 (C=3) images, and the whole-image window (k >= 2*max(H,W)-1 = the Ideal Score
+ * module, idealscore.py:560-636) as a plain sum of rows.  Preferred over cds_ls_partials when supported. */
+int cds_ls_rows_supported(int C, int H, int W, int k);
+int cds_ls_rows_partials(const float* x, int B, int C, int H, int W, int k, const float* beta, const float* images,
+                         const int32_t* idx, const float* logw, int64_t n_sel, int splits, float* m, float* l,
+                         float* acc, void* stream);
+
 /* bbELS edge bands (idealscore.py:256-288): queries whose patch crosses exactly one border vs the zero-padded
  * patches at the same depth and every interior position along the band.  Exact fp32; square images, odd k <= 31.
  * Writes the partials of the edge pixels only. */
