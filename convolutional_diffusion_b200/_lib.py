@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcdscore.so")
+LIB_PATH = os.environ.get("CDS_LIB_PATH", os.path.join(_HERE, "libcdscore.so"))   # override: A/B builds only
 
 KIND = {"LS": 0, "ELS": 1, "bbELS": 2}
 PAD = {"zeros": 0, "circular": 1}

@@ -316,10 +316,16 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               if (C == 1) {
                 acc2[0] = fma2(w, *reinterpret_cast<const float2*>(pv01 + 4 * e), acc2[0]);
               } else {
-                const float4 vv = *reinterpret_cast<const float4*>(pv01 + 4 * e);
-                acc2[0] = fma2(w, make_float2(vv.x, vv.y), acc2[0]);
-                acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
-                if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(pv2 + 2 * e), acc2[2 % C]);
+                if (p.flags & 4) {     // profiling: weighted sums without the centre-pixel table loads
+                  acc2[0] = fma2(w, c1c1, acc2[0]);
+                  acc2[1 % C] = fma2(w, off2, acc2[1 % C]);
+                  if (C > 2) acc2[2 % C] = fma2(w, c1c1, acc2[2 % C]);
+                } else {
+                  const float4 vv = *reinterpret_cast<const float4*>(pv01 + 4 * e);
+                  acc2[0] = fma2(w, make_float2(vv.x, vv.y), acc2[0]);
+                  acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
+                  if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(pv2 + 2 * e), acc2[2 % C]);
+                }
               }
             }
           };

@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
           float* smx = sMax + (T & 1) * (NUM_EPI_WG * 128);
           smx[wg * 128 + q] = (c_lo < c_hi) ? fmaf(dmax, c1, lw) : -INFINITY;
           bar_sync_named(1, 128 * NUM_EPI_WG);
-          float m_tile = fmaxf(fmaxf(smx[q], smx[128 + q]), fmaxf(smx[256 + q], smx[384 + q]));
+          float m_tile = smx[q];
+#pragma unroll
+          for (int w = 1; w < NUM_EPI_WG; ++w) m_tile = fmaxf(m_tile, smx[w * 128 + q]);
           m_run = fmaxf(m_run, m_tile);
           if (buf) mref1 = m_run; else mref0 = m_run;
           // ---- sweep 2: P = 2^(logit - m_run + 14) as fp16, written over the consumed S columns

@@ -9,7 +9,10 @@ namespace umma {
 constexpr int TI = 16, TJ = 8;           // query tile: 16 rows x 8 columns = 128 queries = UMMA M
 constexpr int MAX_STAGES = 2;
 constexpr int MAX_CHUNKS = 8;
-constexpr int NUM_EPI_WG = 4;            // epilogue warpgroups: all of them consume every tile, each a quarter of its columns
+#ifndef CDS_NUM_EPI_WG
+#define CDS_NUM_EPI_WG 4
+#endif
+constexpr int NUM_EPI_WG = CDS_NUM_EPI_WG;            // epilogue warpgroups: all of them consume every tile, each a quarter of its columns
 constexpr int THREADS = 128 + 128 * NUM_EPI_WG;   // 4 control warps + the epilogue warpgroups
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_MMAS = 320;
