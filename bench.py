@@ -162,7 +162,7 @@ def run_ours(args, scales):
     group = dist.group.WORLD if world > 1 else None
     mod = LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=64, schedule=cosine_noise_schedule,
                                 precision=args.precision, process_group=group)
-    machine = ScheduledScoreMachine(mod, in_channels=C, imsize=H, scales=scales, use_cuda_graph=True)
+    machine = ScheduledScoreMachine(mod, in_channels=C, imsize=H, scales=scales, use_cuda_graph=not args.no_graph)
     eng = mod.engine(dev)
     n_per_label = [int((labels == c).sum()) for c in range(NLABELS)]
 
@@ -315,6 +315,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "f16x2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from convolutional_diffusion_b200.scales import load_scales
