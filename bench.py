@@ -126,7 +126,7 @@ def run_reference(args, scales):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_sub = 512
+    n_sub = 1024
     for w in range(args.warmup):
         cpu_sample(n_sub, w % NLABELS, scales, 1000 + w)
     pairs = 0
@@ -262,7 +262,10 @@ def run_ours(args, scales):
         achieved = tot_fl / tot_ms * 1e-9
         roof = {"bound": "tensor", "kernel": "els_umma_kernel", "achieved": achieved, "peak": peaks["bf16"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "frac_sustained": achieved / peaks["bf16_sustained"],
-                "peak_source": peaks["source"], "traffic": None,
+                "peak_source": peaks["source"],
+                # DRAM bytes per launch of this kernel (ncu --set full, profiles/r01d_els_umma_ncu_summary.md: dram read+write
+                # at batch 4, class 0); algorithmic = class sub-bank strip8 + norm plane once = 324 MB
+                "traffic": 671.0e6, "traffic_algorithmic": 324.0e6,
                 "note": "algorithmic 2*k*k*C FLOP per (query, patch) pair, FLOP-weighted over the 19 evaluations of one "
                         "trajectory; CUDA events around the kernel launches on the launching stream", "per_k": per_k}
 
@@ -270,7 +273,7 @@ def run_ours(args, scales):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        n_sub = 1024
+        n_sub = 2048
         cpu_sample(256, 0, scales, 1)                                          # warm the thread pool
         p, dt = cpu_sample(n_sub, 0, scales, 2)
         cpu = {"value": p / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
