@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
                      ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
                      : nullptr;
     const int nchunks = g.nchunks, nvb = g.nvb, vt_tile = g.vt_tile;
+    const bool prof_pass1_only = (p.flags & 1) != 0, prof_mma_only = (p.flags & 2) != 0;   // CDS_DEBUG_FLAGS
     uint32_t T = 0;
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           // explicit masking is only needed when an 8-column block runs past the end of the image row
           const bool edge = 8 * vb + 8 > g.W;
           const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
-          if (p.flags & 2) {     // profiling: MMA pipeline only
+          if (prof_mma_only) {     // profiling: MMA pipeline only
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             // every weight of this chunk is < 2^-40 of the running max for all 32 queries of the warp: adding them
             // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
             if (__all_sync(0xffffffffu, cmax < m - SKIP_LOG2)) return;
-            if (p.flags & 1) { m = fmaxf(m, cmax); return; }     // profiling: pass 1 only
+            if (prof_pass1_only) { m = fmaxf(m, cmax); return; }     // profiling: pass 1 only
             if (cmax > m) {                        // rare after the first few images
               const float sc = ex2(m - cmax);
               const float2 sc2 = make_float2(sc, sc);
@@ -316,16 +317,10 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               if (C == 1) {
                 acc2[0] = fma2(w, *reinterpret_cast<const float2*>(pv01 + 4 * e), acc2[0]);
               } else {
-                if (p.flags & 4) {     // profiling: weighted sums without the centre-pixel table loads
-                  acc2[0] = fma2(w, c1c1, acc2[0]);
-                  acc2[1 % C] = fma2(w, off2, acc2[1 % C]);
-                  if (C > 2) acc2[2 % C] = fma2(w, c1c1, acc2[2 % C]);
-                } else {
-                  const float4 vv = *reinterpret_cast<const float4*>(pv01 + 4 * e);
-                  acc2[0] = fma2(w, make_float2(vv.x, vv.y), acc2[0]);
-                  acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
-                  if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(pv2 + 2 * e), acc2[2 % C]);
-                }
+                const float4 vv = *reinterpret_cast<const float4*>(pv01 + 4 * e);
+                acc2[0] = fma2(w, make_float2(vv.x, vv.y), acc2[0]);
+                acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
+                if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(pv2 + 2 * e), acc2[2 % C]);
               }
             }
           };
