@@ -1,35 +1,38 @@
 // ELS score partials, "P.V" variant: the softmax-weighted sum of the centre pixels also runs on the tensor cores.
 //
 // Same contraction, staging and descriptor aliasing as els_umma.cu (see there).  What differs is the epilogue:
-//   S tile (128 queries x N <= 240 candidates, fp32, TMEM) --epilogue--> P = 2^(logit - m_ref + 14) in fp16, written
-//   back INTO the S buffer (tcgen05.st; P of a 16-column chunk occupies 8 columns at the start of its owner's column
-//   range, so unread S columns are never clobbered) --second UMMA--> O[128 x 16] += P[128 x N] . V'[N x 16], with
-//   V' = (scale*T_c ..., 1, residual planes ...) staged per tile as an fp16 K-major operand by the builder warps.
-//   Column C of O is the softmax denominator.  One warpgroup folds the 16-column O tiles into the per-query
-//   (m, l, acc) state; nothing else of the weighted sum touches the FMA pipe or shared memory.
-// Per tile the four epilogue warpgroups agree on one reference max per query (shared memory + one named barrier),
-// because P.V sums over all columns of the tile.
-// TMEM: S buffers at columns 0 and 240, O tiles at 480 and 496.
+//   S tile (128 queries x N <= 192 candidates, fp32 in TMEM)
+//     --epilogue-->  P = 2^(logit - m_wg), written back IN PLACE over S (tcgen05.st) and read by the tensor core as tf32
+//     --second UMMA (kind::tf32, A from TMEM)-->  O_wg[128 x 16] = P[:, columns of warpgroup wg] . V'[those columns x 16]
+//   V' = (scale*T_c ..., 1, residual planes ...) staged per tile as a K-major fp32 operand by the builder warps; column C
+//   of O is the softmax denominator.  tf32 keeps fp32's exponent range, so P needs no shift and no clamping; its 11-bit
+//   significand rounds every weight by <= 2^-11 relative (numerator and denominator alike).
+// Every epilogue warpgroup owns the 16-column chunks wg, wg+4, ... of a tile, its own running max m_wg and its own
+// 16-column O tile per S buffer, so nothing is exchanged between warpgroups per tile: sweep 1 = max over the own
+// columns, sweep 2 = exp2 + store.  The (m, l, acc) state of a warpgroup is the fold of its O tiles; the four states are
+// merged once at the end.  The weighted sum therefore costs no FMA-pipe instruction and no shared-memory load.
+// TMEM: S buffers at columns 0 and 192, O tiles at 384 + 16*(4*buffer + warpgroup).
 #include "umma_common.cuh"
 
 using namespace umma;
 
 namespace {
 
-constexpr int S_BUF_COLS = 240;
-constexpr int O_COL0 = 480;
-constexpr float P_SHIFT = 14.f;          // P is stored as 2^(logit - m_ref + 14) <= 16384 (fp16 keeps 2^-38 .. 2^14)
+constexpr int S_BUF_COLS = 192;
+constexpr int O_COL0 = 384;
 
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc));
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
@@ -44,11 +47,6 @@ __device__ __forceinline__ void tmem_ld_wait8(uint32_t* r) {
                :
                : "memory");
 }
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 
 template <int C>
 __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_constant__ UmmaParams p) {
@@ -61,12 +59,10 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
   const long long n0 = p.n_sel * split / p.splits, n1 = p.n_sel * (split + 1) / p.splits;
   const int n_img = (int)(n1 - n0);
   const int S = g.stages;
-  const int tiles_per_img = g.nchunks * g.nvb;
-  const int total_tiles = n_img * tiles_per_img;
 
   uint8_t* sA = smem;
   uint8_t* sStage = smem + g.smem_A;
-  float* sMax = reinterpret_cast<float*>(smem + g.smem_A + g.smem_stage);   // [2][NUM_EPI_WG][128] per-tile chunk maxima
+  float* sMax = reinterpret_cast<float*>(smem + g.smem_A + g.smem_stage);   // merge scratch of the warpgroups' final states
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + g.smem_A + g.smem_stage + g.smem_merge + g.smem_table);
   // barriers: full[2], empty[2], vready[2], tfull[2], pready[2], oready[2]; then the TMEM base address
   const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 16, bar_vready = bar_full + 32;
@@ -136,165 +132,168 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *sTmemBase;
 
+  const int units = n_img * g.nchunks;            // staging units (image, row band)
+  const int total_tiles = units * g.nvb;
+
   if (warp == 0) {
-    // =========================== producer (one band per image in this variant: unit == image)
+    // =========================== producer: per (image, band) unit one bulk copy per channel (+ residual plane) of the
+    // band's strip rows, and one of its norm-plane rows
     if (lane == 0) {
-      const uint32_t rows = (uint32_t)min(g.R, g.H), nrows = (uint32_t)min(g.G, g.H);
-      const uint32_t cbytes = rows * g.S1, nbytes = nrows * g.S1;
+      int unit = 0;
       for (int n = 0; n < n_img; ++n) {
-        const int s = n % S;
-        mbar_wait(bar_empty + 8 * s, ((n / S) & 1) ^ 1, 1);
         const long long gi = p.idx[n0 + n];
-        const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
-        mbar_expect_tx(bar_full + 8 * s, g.bank_planes * g.C * cbytes + nbytes);
-        for (int c = 0; c < g.C; ++c) {
-          const size_t src = ((size_t)gi * g.C + c) * g.chan_bytes;
-          bulk_g2s(dst + c * g.R * g.S1, p.bank_hi + src, cbytes, bar_full + 8 * s);
-          if (g.bank_planes > 1)
-            bulk_g2s(dst + g.img_bytes + g.tile_pad + c * g.R * g.S1, p.bank_lo + src, cbytes, bar_full + 8 * s);
+        for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+          const int s = unit % S, u0 = g.chunk_u0[ch];
+          const uint32_t rows = (uint32_t)min(g.R, g.H - u0), nrows = (uint32_t)min(g.G, g.H - u0);
+          const uint32_t cbytes = rows * g.S1, nbytes = nrows * g.S1;
+          mbar_wait(bar_empty + 8 * s, ((unit / S) & 1) ^ 1, 1);
+          const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
+          mbar_expect_tx(bar_full + 8 * s, g.bank_planes * g.C * cbytes + nbytes);
+          for (int c = 0; c < g.C; ++c) {
+            const size_t src = ((size_t)gi * g.C + c) * g.chan_bytes + (size_t)u0 * g.S1;
+            bulk_g2s(dst + c * g.R * g.S1, p.bank_hi + src, cbytes, bar_full + 8 * s);
+            if (g.bank_planes > 1)
+              bulk_g2s(dst + g.img_bytes + g.tile_pad + c * g.R * g.S1, p.bank_lo + src, cbytes, bar_full + 8 * s);
+          }
+          bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.chan_bytes + (size_t)u0 * g.S1, nbytes, bar_full + 8 * s);
         }
-        bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.chan_bytes, nbytes, bar_full + 8 * s);
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer.  Issue order: S(0), S(1), P.V(0), S(2), P.V(1), S(3), ...  S(T+2) reuses
     // the buffer of tile T and is issued after P.V(T), which itself waits until every epilogue warp has finished
-    // reading S(T) and writing P(T); tensor-core operations execute in issue order.
+    // reading S(T) and writing P(T) over it; tensor-core operations execute in issue order.
     const uint64_t a_hi = desc_hi(g.RA), b_hi = desc_hi(g.S1);
-    const uint64_t v_hi = desc_hi(128);                 // V' operand: 8-row groups 128 B apart, K granules 256 B apart
+    const uint64_t v_hi = desc_hi(128);                 // V' operand: 8-row groups 128 B apart
     const uint32_t a_base = smem_u32(sA) >> 4;
     const int nm = g.n_mma;
-    // P.V instruction: D=f32, A/B=f16, K-major, N=16, M=128
-    const uint32_t idesc_pv = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    const int N = 8 * g.G, nck = N >> 4;                // every band has G patch rows: N columns, nck chunks of 16
+    // P.V instruction: D = f32 [4,6)=1, A = B = tf32 [7,10)=[10,13)=2, K-major, N = 16, M = 128; K = 8 per instruction
+    const uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
 
     auto issue_pv = [&](int T) {
-      // tile T of image T / tiles_per_img: chunk / column-block indices, operands, barriers
-      const int n = T / tiles_per_img, tt = T - n * tiles_per_img;
-      const int ch = tt / g.nvb;
-      const int s = n % S;
-      const int buf = T & 1;
-      const int nck = (8 * g.chunk_g[ch]) >> 4;                         // 16-column chunks of this tile
-      const int cw = (nck + NUM_EPI_WG - 1) / NUM_EPI_WG;               // chunks per warpgroup
-      if (tt == 0) mbar_wait(bar_vready + 8 * s, (n / S) & 1, 7);      // V' operands of this image are built
+      const int unit = T / g.nvb, vb = T - unit * g.nvb;
+      const int s = unit % S, buf = T & 1;
+      if (vb == 0) mbar_wait(bar_vready + 8 * s, (unit / S) & 1, 7);        // V' operands of this unit are built
       mbar_wait(bar_pready + 8 * buf, (uint32_t)((T >> 1) & 1), 8);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t vt = (smem_u32(sStage + (size_t)s * g.stage_bytes + g.vt_off) + (uint32_t)tt * g.vt_tile * 4u) >> 4;
-        const uint32_t d_o = tmem_base + O_COL0 + buf * 16;
+        const uint32_t vt = (smem_u32(sStage + (size_t)s * g.stage_bytes + g.vt_off) + (uint32_t)vb * g.vt_tile * 4u) >> 4;
         const uint32_t s_col = tmem_base + buf * S_BUF_COLS;
+        const uint32_t o_col = tmem_base + O_COL0 + buf * (16 * NUM_EPI_WG);
         for (int j = 0; j < nck; ++j) {
-          const int w = j / cw, i = j - w * cw;
-          const uint32_t a_t = s_col + 16 * w * cw + 8 * i;             // P of chunk j (see epilogue)
-          const uint64_t bd = v_hi | (uint64_t)(((vt + (uint32_t)j * 32u) & 0x3FFFu) | (16u << 16));   // +512 B per chunk, LBO 256 B
-          umma_f16_ts(d_o, a_t, bd, idesc_pv, j > 0 ? 1u : 0u);
+          const int w = j % NUM_EPI_WG;                                       // owner of chunk j
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            // 8 candidates = two K granules of 4 fp32 (256 B apart); V' advances 512 B per 8 candidates
+            const uint64_t bd = v_hi | (uint64_t)(((vt + (uint32_t)(2 * j + h) * 32u) & 0x3FFFu) | (16u << 16));
+            umma_tf32_ts(o_col + 16 * w, s_col + 16 * j + 8 * h, bd, idesc_pv, (j >= NUM_EPI_WG || h) ? 1u : 0u);
+          }
         }
         umma_commit(bar_oready + 8 * buf);
-        if (tt == tiles_per_img - 1) umma_commit(bar_empty + 8 * s);    // last reader of this stage
+        if (vb == g.nvb - 1) umma_commit(bar_empty + 8 * s);                  // last reader of this stage
       }
       __syncwarp();
     };
 
     int T = 0;
-    for (int n = 0; n < n_img; ++n) {
-      const int s = n % S;
+    for (int unit = 0; unit < units; ++unit) {
+      const int s = unit % S;
       const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
-      for (int ch = 0; ch < g.nchunks; ++ch) {
-        const uint32_t N = 8u * g.chunk_g[ch];
-        const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
-        for (int vb = 0; vb < g.nvb; ++vb, ++T) {
-          // the pending P.V first: it may be the commit that releases the stage the next image is waiting for
-          if (T >= 2) issue_pv(T - 2);
-          if (ch == 0 && vb == 0) {
-            mbar_wait(bar_full + 8 * s, (n / S) & 1, 2);
-            tc_fence_after();
-          }
-          const int buf = T & 1;
-          const uint32_t d_tmem = tmem_base + buf * S_BUF_COLS;
-          const uint32_t b_base = (stage_addr + vb * 128u) >> 4;
-          if (elect_one()) {
-            {
-              const uint2 e = p.table[0];
-              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 0u);
-            }
-#pragma unroll 4
-            for (int t = 1; t < nm; ++t) {
-              const uint2 e = p.table[t];
-              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 1u);
-            }
-            umma_commit(bar_tfull + 8 * buf);
-          }
-          __syncwarp();
+      for (int vb = 0; vb < g.nvb; ++vb, ++T) {
+        // the pending P.V first: it may be the commit that releases the stage the next unit is waiting for
+        if (T >= 2) issue_pv(T - 2);
+        if (vb == 0) {
+          mbar_wait(bar_full + 8 * s, (unit / S) & 1, 2);
+          tc_fence_after();
         }
+        const int buf = T & 1;
+        const uint32_t d_tmem = tmem_base + buf * S_BUF_COLS;
+        const uint32_t b_base = (stage_addr + vb * 128u) >> 4;
+        if (elect_one()) {
+          {
+            const uint2 e = p.table[0];
+            umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 0u);
+          }
+#pragma unroll 4
+          for (int t = 1; t < nm; ++t) {
+            const uint2 e = p.table[t];
+            umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 1u);
+          }
+          umma_commit(bar_tfull + 8 * buf);
+        }
+        __syncwarp();
       }
     }
     if (total_tiles >= 2) issue_pv(total_tiles - 2);
     issue_pv(total_tiles - 1);
   } else if (warp == 2 || warp == 3) {
-    // =========================== builders: V'^T operand of every tile of the staged image, fp16, K-major no-swizzle:
-    // element (row nrow, candidate column r) at  (r/8)*256 + (nrow/8)*128 + (nrow%8)*16 + (r%8)*2  bytes;
-    // rows 0..C-1 = scale*T_c (centre pixel), row C = 1 (softmax denominator), rows C+1.. = residual plane
+    // =========================== builders: V' operand of every tile of the staged band, fp32 (read as tf32), K-major
+    // no-swizzle: element (row nrow, candidate column r) at (r/4)*256 + (nrow/8)*128 + (nrow%8)*16 + (r%4)*4 bytes;
+    // rows 0..C-1 = scale*T_c (centre pixel), row C = 1 (softmax denominator), rows C+1.. = residual plane, rest 0
     const int bt = tid - 64;   // 0..63
+    const int N = 8 * g.G;
+    int unit = 0;
     for (int n = 0; n < n_img; ++n) {
-      const int s = n % S;
-      mbar_wait(bar_full + 8 * s, (n / S) & 1, 6);
-      const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
-      uint8_t* vt = sStage + (size_t)s * g.stage_bytes + g.vt_off;
-      int tt = 0;
-      for (int ch = 0; ch < g.nchunks; ++ch) {
-        const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
-        for (int vb = 0; vb < g.nvb; ++vb, ++tt) {
-          uint8_t* vtile = vt + (size_t)tt * g.vt_tile * 4;
-          // one thread per (candidate, row group): 16 half values of one candidate = rows 0..7 (group 0) / 8..15 (group 1)
-          for (int e = bt; e < 2 * N; e += 64) {
-            const int r = e >> 1, grp = e & 1;
+      for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+        const int s = unit % S, u0 = g.chunk_u0[ch];
+        mbar_wait(bar_full + 8 * s, (unit / S) & 1, 6);
+        const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
+        uint8_t* vt = sStage + (size_t)s * g.stage_bytes + g.vt_off;
+        for (int vb = 0; vb < g.nvb; ++vb) {
+          uint8_t* vtile = vt + (size_t)vb * g.vt_tile * 4;
+          for (int r = bt; r < N; r += 64) {
             const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
-            const bool valid = (u < g.Ph) && (v < g.Pw);
-            __half rows[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) rows[q] = __float2half_rn(0.f);
-            if (grp == 0 && valid) {
+            float rows[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (u < g.Ph && v < g.Pw) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
                 const size_t go = ((size_t)(c * g.R + (u - u0) + g.d) * g.W + (v + g.d)) * 16;
-                rows[c] = *reinterpret_cast<const __half*>(st + go);
-                if (g.bank_planes > 1) rows[C + 1 + c] = *reinterpret_cast<const __half*>(st + g.img_bytes + g.tile_pad + go);
+                rows[c] = __half2float(*reinterpret_cast<const __half*>(st + go));
+                if (g.bank_planes > 1)
+                  rows[C + 1 + c] = __half2float(*reinterpret_cast<const __half*>(st + g.img_bytes + g.tile_pad + go));
               }
-              rows[C] = __float2half_rn(1.f);
+              rows[C] = 1.f;
             }
-            __half* dst = reinterpret_cast<__half*>(vtile + (size_t)(r >> 3) * 256 + grp * 128) + (r & 7);
+            float* dst = reinterpret_cast<float*>(vtile + (size_t)(r >> 2) * 256) + (r & 3);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q * 8] = rows[q];
+            for (int q = 0; q < 8; ++q) {
+              dst[q * 4] = rows[q];            // row group 0 (rows 0..7)
+              dst[32 + q * 4] = 0.f;           // row group 1 (rows 8..15) is unused
+            }
           }
         }
+        fence_proxy_async();           // generic-proxy writes above are read by the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_vready + 8 * s);
       }
-      fence_proxy_async();           // generic-proxy writes above are read by the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_vready + 8 * s);
     }
   } else {
-    // =========================== epilogue
-    // Tile T sits in S buffer T & 1.  Warpgroup wg owns the contiguous chunks [wg*cw, wg*cw + cw) of 16 columns.
+    // =========================== epilogue: tile T sits in S buffer T & 1; warpgroup wg owns chunks wg, wg+4, ...
     const int wg = (warp - 4) >> 2, q = tid - 128 - wg * 128;   // q = query row = TMEM lane
     const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     const float c1 = CDS_LOG2E * a / beta * inv_scale;
     const float2 c1c1 = make_float2(c1, c1);
-    float m_run = -INFINITY;                    // common to the four threads that share a query row
-    // folded state (warpgroup 0 only)
-    float m_acc = -INFINITY, l = 0.f, acc[C];
+    const int N = 8 * g.G;
+    const bool has_cols = 16 * wg < N;                          // a narrow tile may leave the last warpgroups idle
+    float m_run = -INFINITY;                                    // running max over this warpgroup's columns
+    float m_acc = -INFINITY, l = 0.f, acc[C];                   // fold of this warpgroup's O tiles
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
-    float mref0 = 0.f, mref1 = 0.f;             // reference max used for the P of the tile in each S buffer
+    float mref0 = 0.f, mref1 = 0.f;                             // m_run used for the P of the tile in each S buffer
     float* dbg = (p.dbg && split == 0 && qi < g.H && qj < g.W)
                      ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
                      : nullptr;
 
-    auto fold = [&](int T) {                    // O tile of tile T -> (m_acc, l, acc); warpgroup 0 only
+    auto fold = [&](int T) {                                    // O tile of (tile T, this warpgroup) -> (m_acc, l, acc)
       const int buf = T & 1;
       mbar_wait(bar_oready + 8 * buf, (uint32_t)((T >> 1) & 1), 9);
       tc_fence_after();
+      if (!has_cols) return;
       uint32_t o[8];
-      tmem_ld8(tmem_base + O_COL0 + buf * 16 + lane_addr, o);
+      tmem_ld8(tmem_base + O_COL0 + buf * (16 * NUM_EPI_WG) + 16 * wg + lane_addr, o);
       tmem_ld_wait8(o);
       const float mr = buf ? mref1 : mref0;
       const float mn = fmaxf(m_acc, mr);
@@ -310,25 +309,23 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
       m_acc = mn;
     };
 
-    int T = 0;
+    int T = 0, unit = 0;
     for (int n = 0; n < n_img; ++n) {
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
       const bool dump = (dbg != nullptr) && n == 0;
-      for (int ch = 0; ch < g.nchunks; ++ch) {
-        const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
-        const int nck = N >> 4, cw = (nck + NUM_EPI_WG - 1) / NUM_EPI_WG;
-        const int c_lo = 16 * wg * cw, c_hi = min(N, c_lo + 16 * cw);     // this warpgroup's columns
+      for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+        const int u0 = g.chunk_u0[ch];
         for (int vb = 0; vb < g.nvb; ++vb, ++T) {
           const int buf = T & 1;
-          if (wg == 0 && T >= 2) fold(T - 2);     // frees the O tile of this buffer before P.V(T) can be issued
+          if (T >= 2) fold(T - 2);                // frees this warpgroup's O tile of the buffer before P.V(T) is issued
           mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
           tc_fence_after();
           const uint32_t taddr = tmem_base + buf * S_BUF_COLS + lane_addr;
           const bool edge = 8 * vb + 8 > g.W;
           const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
-          // ---- sweep 1: this warpgroup's best logit per query
+          // ---- sweep 1: best logit of this warpgroup's columns (c1 > 0, so the max commutes with the affine map)
           float dmax = -INFINITY;
-          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+          for (int c0 = 16 * wg; c0 < N; c0 += 16 * NUM_EPI_WG) {
             uint32_t r[16];
             tmem_ld16(taddr + c0, r);
             tmem_ld_wait16(r);
@@ -347,22 +344,14 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
               }
             }
           }
-          // ---- one reference max per query for the whole tile (P.V sums over all of its columns)
-          float* smx = sMax + (T & 1) * (NUM_EPI_WG * 128);
-          smx[wg * 128 + q] = (c_lo < c_hi) ? fmaf(dmax, c1, lw) : -INFINITY;
-          bar_sync_named(1, 128 * NUM_EPI_WG);
-          float m_tile = smx[q];
-#pragma unroll
-          for (int w = 1; w < NUM_EPI_WG; ++w) m_tile = fmaxf(m_tile, smx[w * 128 + q]);
-          m_run = fmaxf(m_run, m_tile);
+          if (has_cols) m_run = fmaxf(m_run, fmaf(dmax, c1, lw));
           if (buf) mref1 = m_run; else mref0 = m_run;
-          // ---- sweep 2: P = 2^(logit - m_run + 14) as fp16, written over the consumed S columns
-          const float off = lw - m_run + P_SHIFT;
+          // ---- sweep 2: P = 2^(logit - m_run), stored over the S columns it came from
+          const float off = (m_run == -INFINITY) ? -INFINITY : lw - m_run;   // nothing valid seen yet: all weights 0
           const float2 off2 = make_float2(off, off);
           const float skip_d = (m_run - SKIP_LOG2 - lw) / c1;     // accumulator value below which a weight is < 2^-40
-          int i = 0;
-          for (int c0 = c_lo; c0 < c_hi; c0 += 16, ++i) {
-            uint32_t r[16], pk[8];
+          for (int c0 = 16 * wg; c0 < N; c0 += 16 * NUM_EPI_WG) {
+            uint32_t r[16];
             tmem_ld16(taddr + c0, r);
             tmem_ld_wait16(r);
             if (edge) {
@@ -376,15 +365,16 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
             cm = fmaxf(cm, __uint_as_float(r[15]));
             if (__all_sync(0xffffffffu, cm < skip_d)) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) pk[e] = 0u;
+              for (int e = 0; e < 16; ++e) r[e] = 0u;
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float2 ar = fma2(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), c1c1, off2);
-                pk[e] = pack_f16x2(ex2(ar.x), ex2(ar.y));
+                r[2 * e] = __float_as_uint(ex2(ar.x));
+                r[2 * e + 1] = __float_as_uint(ex2(ar.y));
               }
             }
-            tmem_st8(taddr + c_lo + 8 * i, pk);
+            tmem_st16(taddr + c0, r);
           }
           tmem_st_wait();
           tc_fence_before();
@@ -393,19 +383,42 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
         }
       }
     }
-    if (wg == 0) {
-      if (total_tiles >= 2) fold(total_tiles - 2);
-      fold(total_tiles - 1);
-      if (qi < g.H && qj < g.W) {
-        // undo the 2^14 shift of P and the bank scale of V'
-        const float k_l = exp2f(-P_SHIFT), k_a = k_l * inv_scale;
-        const int HW = g.H * g.W, pix = qi * g.W + qj;
-        const size_t o = ((size_t)split * p.B + b) * HW + pix;
-        p.m[o] = m_acc;
-        p.l[o] = l * k_l;
+    if (total_tiles >= 2) fold(total_tiles - 2);
+    fold(total_tiles - 1);
+    // undo the bank scale of V', merge the warpgroups' states and write this split's partials
 #pragma unroll
-        for (int c = 0; c < C; ++c) p.acc[(((size_t)split * p.B + b) * C + c) * HW + pix] = acc[c] * k_a;
+    for (int c = 0; c < C; ++c) acc[c] *= inv_scale;
+    float* sMerge = sMax;                                    // [NUM_EPI_WG-1][128][2+C]
+    if (wg > 0) {
+      float* dst = sMerge + ((wg - 1) * 128 + q) * (2 + C);
+      dst[0] = m_acc;
+      dst[1] = l;
+#pragma unroll
+      for (int c = 0; c < C; ++c) dst[2 + c] = acc[c];
+    }
+    bar_sync_named(1, 128 * NUM_EPI_WG);
+    if (wg == 0 && qi < g.H && qj < g.W) {
+      float M = m_acc;
+#pragma unroll
+      for (int w = 1; w < NUM_EPI_WG; ++w) M = fmaxf(M, sMerge[((w - 1) * 128 + q) * (2 + C)]);
+      const float w0 = (m_acc == -INFINITY) ? 0.f : ex2(m_acc - M);
+      float L = l * w0, A[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) A[c] = acc[c] * w0;
+#pragma unroll
+      for (int w = 1; w < NUM_EPI_WG; ++w) {
+        const float* src = sMerge + ((w - 1) * 128 + q) * (2 + C);
+        const float ww = (src[0] == -INFINITY) ? 0.f : ex2(src[0] - M);
+        L = fmaf(src[1], ww, L);
+#pragma unroll
+        for (int c = 0; c < C; ++c) A[c] = fmaf(src[2 + c], ww, A[c]);
       }
+      const int HW = g.H * g.W, pix = qi * g.W + qj;
+      const size_t o = ((size_t)split * p.B + b) * HW + pix;
+      p.m[o] = M;
+      p.l[o] = L;
+#pragma unroll
+      for (int c = 0; c < C; ++c) p.acc[(((size_t)split * p.B + b) * C + c) * HW + pix] = A[c];
     }
   }
   tc_fence_before();

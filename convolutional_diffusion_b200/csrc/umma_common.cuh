@@ -37,7 +37,7 @@ struct UmmaGeom {
   int np_off;         // offset of the norm plane inside a stage
   int vt_off;         // offset of the centre-pixel table inside a stage
   int vt_tile;        // floats per tile of that table: [N/2 pairs][4] (v0,v1) + [N/2][2] (v2); PV variant: the
-                      // fp16 UMMA operand V'^T [16 rows][N] K-major = N*32 bytes per tile
+                      // fp32 (tf32) UMMA operand V'^T [16 rows][N] K-major = N*64 bytes per tile
   int pv;             // 1 = geometry of the P.V (weighted sum on the tensor cores) variant
   int stage_bytes;
   int stages;
@@ -246,10 +246,10 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
     if (G > ((g.Ph + 1) & ~1)) continue;
     const int nch = (g.Ph + G - 1) / G;
     if (nch > MAX_CHUNKS || nch * G > H) continue;          // norm-plane / strip rows of a partial last band must exist
-    if (pv && (nch != 1 || 8 * G > 240)) continue;          // P.V variant: one band per image, two S buffers + O tiles in TMEM
+    if (pv && 8 * G > 192) continue;                        // P.V variant: two S buffers + 2 x 4 O tiles of 16 columns in TMEM
     const int R = G + halo;
     const int band = C * R * g.S1;
-    const int vt_tile = pv ? 8 * G * 32 / 4 : 8 * G / 2 * 6;
+    const int vt_tile = pv ? 8 * G * 16 : 8 * G / 2 * 6;
     const int stage = (bank_planes * (band + g.tile_pad) + G * g.S1 + g.tile_pad + g.nvb * vt_tile * 4 + 127) / 128 * 128;
     const int st = fixed + 2 * stage <= 227 * 1024 ? 2 : (fixed + stage <= 227 * 1024 ? 1 : 0);
     if (st > bestStages) { bestStages = st; bestG = G; }
@@ -264,7 +264,7 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.np_bytes = g.G * g.S1;
   g.np_off = bank_planes * (g.img_bytes + g.tile_pad);
   g.vt_off = g.np_off + g.np_bytes + g.tile_pad;
-  g.vt_tile = pv ? 8 * g.G * 32 / 4 : 8 * g.G / 2 * 6;      // floats per tile (see UmmaGeom::vt_tile)
+  g.vt_tile = pv ? 8 * g.G * 16 : 8 * g.G / 2 * 6;          // floats per tile (see UmmaGeom::vt_tile)
   g.stage_bytes = (g.vt_off + g.nvb * g.vt_tile * 4 + 127) / 128 * 128;
   g.stages = bestStages;
 
