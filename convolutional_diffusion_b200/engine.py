@@ -94,9 +94,20 @@ class ScoreEngine:
                 best, best_eff = s, eff
         return int(max(1, min(best, n_sel)))
 
+    def _empty_shard(self, tag, B):
+        """A rank whose interleaved shard holds no image of the requested class contributes the neutral element of the
+        log-sum-exp merge (m = -inf, l = 0, acc = 0); the kernels are not launched."""
+        P = self._partials(tag, 1, B)
+        P.m.fill_(float("-inf"))
+        P.l.zero_()
+        P.acc.zero_()
+        return P
+
     # ---- kernels -------------------------------------------------------------------------------
     def simt_partials(self, kind, pad, x, beta, k, sel, region=0, tag="simt"):
         idx, logw, n_sel = sel
+        if n_sel == 0:
+            return self._empty_shard(tag, x.shape[0])
         b = self.bank
         B = x.shape[0]
         tiles = (b.H * b.W + 127) // 128
@@ -120,6 +131,8 @@ class ScoreEngine:
     def ls_partials(self, x, beta, k, sel, tag="ls"):
         """Bank-streaming LS kernel (csrc/ls_kernel.cu): the bank slice of every CTA is read once."""
         idx, logw, n_sel = sel
+        if n_sel == 0:
+            return self._empty_shard(tag, x.shape[0])
         b = self.bank
         B = x.shape[0]
         rows = bool(self.lib.cds_ls_rows_supported(b.C, b.H, b.W, k))
@@ -140,6 +153,8 @@ class ScoreEngine:
     def edge_partials(self, x, beta, k, sel, tag="edge"):
         """bbELS edge bands (csrc/bbels_edge.cu); writes the edge pixels of the partials only."""
         idx, logw, n_sel = sel
+        if n_sel == 0:
+            return self._empty_shard(tag, x.shape[0])
         b = self.bank
         B = x.shape[0]
         S = int(max(1, min(n_sel // 8, (4 * sm_count(self.device)) // (4 * B))))
@@ -152,6 +167,8 @@ class ScoreEngine:
 
     def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma"):
         idx, logw, n_sel = sel
+        if n_sel == 0:
+            return self._empty_shard(tag, x.shape[0])
         b = self.bank
         B = x.shape[0]
         hi, lo, scale = b.strip8()

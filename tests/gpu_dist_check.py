@@ -30,6 +30,17 @@ def main():
             err = float((s0 - s1).abs().max())
             worst = max(worst, err)
             assert err < 1e-3, (cls.__name__, label, err)
+    # a class with a single image: with two ranks one shard is empty and must contribute the neutral element
+    few_labels = labels.clone()
+    few_labels[few_labels == 9] = 0
+    few_labels[7] = 9
+    for cls in (LocalEquivScoreModule, LocalEquivBordersScoreModule):
+        full = cls((bank, few_labels), kernel_size=5, batch_size=64, schedule=cosine_noise_schedule)
+        shard = cls((bank, few_labels), kernel_size=5, batch_size=64, schedule=cosine_noise_schedule,
+                    process_group=dist.group.WORLD)
+        s0 = full(torch.full((2,), 0.5), x, label=torch.tensor([9]), device=dev)
+        s1 = shard(torch.full((2,), 0.5), x, label=torch.tensor([9]), device=dev)
+        assert float((s0 - s1).abs().max()) < 1e-3, "empty shard"
     scales = [3, 3, 3, 5, 7, 9, 13, 17]
     full = LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=64, schedule=cosine_noise_schedule)
     shard = LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=64, schedule=cosine_noise_schedule,
