@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     const float c1 = CDS_LOG2E * a / beta * inv_scale;   // accumulator -> log2-unit logit
     const float2 c1c1 = make_float2(c1, c1);
+    // the norm-plane marker suppresses invalid positions by 2^-(log2e * a^2/(2 beta) * 3 * INVALID_NORM); when beta -> 1 that
+    // factor fades (a -> 0), so fall back to explicit column masking
+    const bool weak_marker = CDS_LOG2E * a * a / (2.f * beta) * 3.f * INVALID_NORM < 64.f;
     // softmax state; even / odd columns accumulate separately (packed math, shorter dependency chains)
     float m = -INFINITY;
     float2 l2 = make_float2(0.f, 0.f), acc2[C];
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
           // partial blocks inside the row and rounded-up patch rows are already masked by the norm plane's marker;
           // explicit masking is only needed when an 8-column block runs past the end of the image row
-          const bool edge = 8 * vb + 8 > g.W;
+          const bool edge = weak_marker || 8 * vb + 8 > g.W;
           const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
           if (prof_mma_only) {     // profiling: MMA pipeline only
             tc_fence_before();

@@ -276,6 +276,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     const float c1 = CDS_LOG2E * a / beta * inv_scale;
     const float2 c1c1 = make_float2(c1, c1);
+    // the norm-plane marker suppresses invalid positions by 2^-(log2e * a^2/(2 beta) * 3 * INVALID_NORM); when beta -> 1 that
+    // factor fades (a -> 0), so fall back to explicit column masking
+    const bool weak_marker = CDS_LOG2E * a * a / (2.f * beta) * 3.f * INVALID_NORM < 64.f;
     const int N = 8 * g.G;
     const bool has_cols = 16 * wg < N;                          // a narrow tile may leave the last warpgroups idle
     float m_run = -INFINITY;                                    // running max over this warpgroup's columns
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_pv_kernel(const __grid_co
           mbar_wait(bar_tfull + 8 * buf, (uint32_t)((T >> 1) & 1), 5);
           tc_fence_after();
           const uint32_t taddr = tmem_base + buf * S_BUF_COLS + lane_addr;
-          const bool edge = 8 * vb + 8 > g.W;
+          const bool edge = weak_marker || 8 * vb + 8 > g.W;
           const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
           // ---- sweep 1: best logit of this warpgroup's columns (c1 > 0, so the max commutes with the affine map)
           float dmax = -INFINITY;

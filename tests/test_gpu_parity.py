@@ -316,3 +316,21 @@ def test_els_64x64_band_staging(k, t):
     mu = _mu_from_score(s, x[0].double().numpy(), beta)
     mu_o = _oracle_mu("ELS", x[0].numpy(), bank.numpy(), labels.numpy(), None, beta, k, 8)
     assert np.max(np.abs(mu - mu_o)) < MU_TOL
+
+
+@pytest.mark.parametrize("variant", ["v2", "pv"])
+def test_els_at_t_equal_one(variant):
+    """t = 1 (beta = 0.9998, a = 0.012, used by scales_calibration): the norm-plane marker no longer suppresses invalid
+    patch positions by itself, the kernels must mask them explicitly."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    bank, labels = synthetic_bank(24, 3, 32, nlabels=2, seed=41)
+    beta = float(so.cosine_beta(1.0))
+    x = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(2))
+    for k in (3, 9):
+        mod = _make("ELS", (bank, labels), k, 8, None)
+        mod.engine("cuda").els_variant = variant
+        s = mod(torch.tensor([1.0]), x.cuda(), device=torch.device("cuda")).cpu().double().numpy()[0]
+        mu = _mu_from_score(s, x[0].double().numpy(), beta)
+        mu_o = _oracle_mu("ELS", x[0].numpy(), bank.numpy(), labels.numpy(), None, beta, k, 8)
+        assert np.max(np.abs(mu - mu_o)) < MU_TOL, (k, np.max(np.abs(mu - mu_o)))
