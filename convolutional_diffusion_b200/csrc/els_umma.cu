@@ -25,6 +25,7 @@
 //   * Epilogue = flash softmax in two passes per 16-column chunk: (1) tcgen05.ld + 3-input max; a chunk whose
 //     best logit is 2^-40 below the running max for all 32 queries of the warp is skipped; (2) packed f32x2
 //     fma -> ex2 -> weighted sums.
+#include <type_traits>
 #include "umma_common.cuh"
 
 using namespace umma;
@@ -275,9 +276,10 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
             continue;
           }
-          auto chunk = [&](uint32_t* r, int c0) {
+          // `slow` = tiles that need explicit column masking or the debug dump; the common path carries neither check
+          auto chunk = [&](uint32_t* r, int c0, auto slow) {
             // columns that are not valid patches are forced to -FLT_MAX: they never win the max and get weight 0
-            if (edge) {
+            if (decltype(slow)::value && edge) {
 #pragma unroll
               for (int e = 0; e < 16; ++e)
                 if (((c0 + e) & 7) >= nval_v || ((c0 + e) >> 3) >= nval_u) r[e] = 0xff7fffffu;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             for (int e = 3; e < 15; e += 2) dmax = max3(dmax, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
             dmax = fmaxf(dmax, __uint_as_float(r[15]));
             const float cmax = fmaf(dmax, c1, lw);
-            if (dump) {
+            if (decltype(slow)::value && dump) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 const int u = u0 + ((c0 + e) >> 3), v = 8 * vb + ((c0 + e) & 7);
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             }
           };
           // software-pipelined TMEM reads: the next chunk's tcgen05.ld is in flight while this one is consumed
-          {
+          auto sweep = [&](auto slow) {
             uint32_t ra[16], rb[16];
             int c0 = 16 * wg;
             if (c0 < N) tmem_ld16(taddr + c0, ra);
@@ -336,14 +338,16 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               tmem_ld_wait16(ra);
               const int c1n = c0 + 16 * NUM_EPI_WG;
               if (c1n < N) tmem_ld16(taddr + c1n, rb);
-              chunk(ra, c0);
+              chunk(ra, c0, slow);
               if (c1n >= N) break;
               tmem_ld_wait16(rb);
               c0 = c1n + 16 * NUM_EPI_WG;
               if (c0 < N) tmem_ld16(taddr + c0, ra);
-              chunk(rb, c1n);
+              chunk(rb, c1n, slow);
             }
-          }
+          };
+          if (edge || dump) sweep(std::true_type{});
+          else sweep(std::false_type{});
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);

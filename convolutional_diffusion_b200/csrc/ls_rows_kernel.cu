@@ -17,7 +17,16 @@
 namespace {
 
 constexpr int SB = 2;      // samples per CTA (softmax states and x live in registers)
-__host__ __device__ constexpr int images_per_round(int C) { return C == 1 ? 8 : 4; }
+#ifndef CDS_LS_IB_C1
+#define CDS_LS_IB_C1 8
+#endif
+#ifndef CDS_LS_IB_C3
+#define CDS_LS_IB_C3 4
+#endif
+#ifndef CDS_LS_MINBLOCKS
+#define CDS_LS_MINBLOCKS 1
+#endif
+__host__ __device__ constexpr int images_per_round(int C) { return C == 1 ? CDS_LS_IB_C1 : CDS_LS_IB_C3; }
 
 struct LsParams {
   int B, C, H, W, k, splits;
@@ -52,7 +61,7 @@ __device__ __forceinline__ float row_box(float e, int d, int lane) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(1024) ls_rows_kernel(LsParams p) {
+__global__ void __launch_bounds__(1024, CDS_LS_MINBLOCKS) ls_rows_kernel(LsParams p) {
   extern __shared__ float smem[];
   constexpr int IB = images_per_round(C);
   const int H = p.H, W = p.W, k = p.k, HW = H * W;
