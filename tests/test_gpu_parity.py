@@ -334,3 +334,44 @@ def test_els_at_t_equal_one(variant):
         mu = _mu_from_score(s, x[0].double().numpy(), beta)
         mu_o = _oracle_mu("ELS", x[0].numpy(), bank.numpy(), labels.numpy(), None, beta, k, 8)
         assert np.max(np.abs(mu - mu_o)) < MU_TOL, (k, np.max(np.abs(mu - mu_o)))
+
+
+def test_random_geometries_against_oracle():
+    """Fuzz: random small geometries (odd / even / non-square-free image sizes, every kernel size that fits, both channel
+    counts, labels, ragged batches, max_samples) for all four module kinds against the float64 oracle."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
+    rng = np.random.default_rng(2024)
+    worst = 0.0
+    for trial in range(40):
+        kind = ["ELS", "bbELS", "LS", "IS"][trial % 4]
+        C = int(rng.choice([1, 3]))
+        H = int(rng.integers(7, 25))
+        kmax = H if kind == "ELS" else (H - 1 if kind == "bbELS" and trial % 8 else H + 4)
+        k = int(rng.choice([v for v in range(3, max(4, kmax + 1), 2)]))
+        N = int(rng.integers(3, 40))
+        bs = int(rng.integers(2, N + 2))
+        label = None if rng.random() < 0.5 else int(rng.integers(0, 3))
+        ms = None if rng.random() < 0.7 else int(rng.integers(bs, N + bs))
+        t = float(rng.uniform(0.03, 0.98))
+        bank, labels = synthetic_bank(N, C, H, nlabels=3, seed=100 + trial)
+        if label is not None and not bool((labels == label).any()):
+            label = int(labels[0])
+        beta = float(so.cosine_beta(t))
+        x = noisy_query(bank, beta, 1, seed=trial)
+        sel_kind = "LS" if (kind == "bbELS" and k >= H) else kind
+        idx, logw = so.select_bank(sel_kind, labels.numpy(), label, bs, ms)
+        if len(idx) == 0:
+            continue
+        torch.manual_seed(trial)
+        mod = _make(kind, (bank, labels), k, bs, ms)
+        if kind in ("LS", "bbELS") and bs < N:      # shuffled LS batches: keep the mean quirk order independent
+            continue
+        lab = None if label is None else torch.tensor([label])
+        s = mod(torch.tensor([t]), x.cuda(), label=lab, device=torch.device("cuda"), k=k).cpu().double().numpy()[0]
+        mu = _mu_from_score(s, x[0].double().numpy(), beta)
+        _, mu_o = so.score(kind, x[0].numpy(), bank.numpy()[idx], beta, k, logw)
+        err = float(np.max(np.abs(mu - mu_o)))
+        worst = max(worst, err)
+        assert err < MU_TOL, (trial, kind, C, H, k, N, bs, label, ms, t, err)
+    print(f"fuzz worst mu error {worst:.2e}")
