@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
                      ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
                      : nullptr;
     const int nchunks = g.nchunks, nvb = g.nvb, vt_tile = g.vt_tile;
+#ifdef CDS_PROFILE_SWITCHES
     const bool prof_pass1_only = (p.flags & 1) != 0, prof_mma_only = (p.flags & 2) != 0;   // CDS_DEBUG_FLAGS
+#endif
     uint32_t T = 0;
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
@@ -262,20 +264,24 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         for (int vb = 0; vb < nvb; ++vb, ++T, vtile += vt_tile) {
           const uint32_t buf = T & 1u;
           const float* v01 = vtile;
-          const float* v2 = vtile + 2 * N;
           mbar_wait(bar_tfull + 8 * buf, (T >> 1) & 1u, 5);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + buf * 256 + lane_addr;
+          uint32_t taddr = tmem_base + buf * 256 + lane_addr;
+          int Nr = N;
+          asm volatile("" : "+r"(taddr), "+r"(Nr));   // opaque: keep in registers instead of recomputing per chunk
+          const float* v2 = vtile + 2 * Nr;
           // partial blocks inside the row and rounded-up patch rows are already masked by the norm plane's marker;
           // explicit masking is only needed when an 8-column block runs past the end of the image row
           const bool edge = weak_marker || 8 * vb + 8 > g.W;
           const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - u0;
+#ifdef CDS_PROFILE_SWITCHES
           if (prof_mma_only) {     // profiling: MMA pipeline only
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
             continue;
           }
+#endif
           // `slow` = tiles that need explicit column masking or the debug dump; the common path carries neither check
           auto chunk = [&](uint32_t* r, int c0, auto slow) {
             // columns that are not valid patches are forced to -FLT_MAX: they never win the max and get weight 0
@@ -300,7 +306,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             // every weight of this chunk is < 2^-40 of the running max for all 32 queries of the warp: adding them
             // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
             if (__all_sync(0xffffffffu, cmax < m - SKIP_LOG2)) return;
+#ifdef CDS_PROFILE_SWITCHES
             if (prof_pass1_only) { m = fmaxf(m, cmax); return; }     // profiling: pass 1 only
+#endif
             if (cmax > m) {                        // rare after the first few images
               const float sc = ex2(m - cmax);
               const float2 sc2 = make_float2(sc, sc);
@@ -333,16 +341,16 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           auto sweep = [&](auto slow) {
             uint32_t ra[16], rb[16];
             int c0 = 16 * wg;
-            if (c0 < N) tmem_ld16(taddr + c0, ra);
-            while (c0 < N) {
+            if (c0 < Nr) tmem_ld16(taddr + c0, ra);
+            while (c0 < Nr) {
               tmem_ld_wait16(ra);
               const int c1n = c0 + 16 * NUM_EPI_WG;
-              if (c1n < N) tmem_ld16(taddr + c1n, rb);
+              if (c1n < Nr) tmem_ld16(taddr + c1n, rb);
               chunk(ra, c0, slow);
-              if (c1n >= N) break;
+              if (c1n >= Nr) break;
               tmem_ld_wait16(rb);
               c0 = c1n + 16 * NUM_EPI_WG;
-              if (c0 < N) tmem_ld16(taddr + c0, ra);
+              if (c0 < Nr) tmem_ld16(taddr + c0, ra);
               chunk(rb, c1n, slow);
             }
           };
