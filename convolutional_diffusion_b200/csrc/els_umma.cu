@@ -202,8 +202,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         float* vt = reinterpret_cast<float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
         for (int vb = 0; vb < g.nvb; ++vb) {
-          float* v01 = vt + (size_t)vb * g.vt_tile;
-          float* v2 = v01 + 2 * N;
+          float* vtab = vt + (size_t)vb * g.vt_tile;   // [16-column chunk][channel][t4][column pair h][lo]
           for (int r = bt; r < N; r += 64) {
             const int u = u0 + (r >> 3), v = 8 * vb + (r & 7);
             float vals[3] = {0.f, 0.f, 0.f};
@@ -217,10 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
                 vals[c] = t * inv_scale;
               }
             }
-            const int pr = r >> 1, hf = r & 1;
-            v01[4 * pr + hf] = vals[0];
-            v01[4 * pr + 2 + hf] = vals[1];
-            v2[2 * pr + hf] = vals[2];
+            const int slot = ((r & 7) >> 1) * 4 + ((r >> 3) & 1) * 2 + (r & 1);
+#pragma unroll
+            for (int c = 0; c < C; ++c) vtab[((r >> 4) * C + c) * 16 + slot] = vals[c];
           }
         }
         __syncwarp();
@@ -231,22 +229,29 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     // =========================== epilogue
     // Tile T sits in TMEM buffer T & 1; while the four warpgroups drain it (warpgroup wg takes the 16-column chunks
     // wg, wg+4, ...), the MMA warp fills the other buffer with tile T+1.
-    const int wg = (warp - 4) >> 2, q = tid - 128 - wg * 128;   // q = query row = TMEM lane
-    const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
-    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+    // TMEM is read with the 16x256b shape: per 16-column chunk a thread holds FOUR query rows (tr, tr+8, tr+16, tr+24 of
+    // its warp's 32 lanes) x FOUR columns (the pairs 2*t4 and 8+2*t4), so one 16-byte load of centre pixels per channel
+    // serves 16 (query, candidate) pairs: a quarter of the shared-memory traffic of the row-per-thread 32x32b shape, and
+    // shared-memory bandwidth (these loads + the UMMA operand reads) is what bounds the kernel.
+    const int wg = (warp - 4) >> 2, lq = warp & 3;
+    const int t4 = lane & 3, tr = lane >> 2;
+    const uint32_t lane_addr = ((uint32_t)(lq * 32)) << 16;
     const float c1 = CDS_LOG2E * a / beta * inv_scale;   // accumulator -> log2-unit logit
     const float2 c1c1 = make_float2(c1, c1);
     // the norm-plane marker suppresses invalid positions by 2^-(log2e * a^2/(2 beta) * 3 * INVALID_NORM); when beta -> 1 that
     // factor fades (a -> 0), so fall back to explicit column masking
     const bool weak_marker = CDS_LOG2E * a * a / (2.f * beta) * 3.f * INVALID_NORM < 64.f;
-    // softmax state; even / odd columns accumulate separately (packed math, shorter dependency chains)
-    float m = -INFINITY;
-    float2 l2 = make_float2(0.f, 0.f), acc2[C];
+    // softmax state of row j = tr + 8*j over this thread's columns; even / odd columns accumulate separately (packed math)
+    float m4[4];
+    float2 l2[4], acc2[4][C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc2[c] = make_float2(0.f, 0.f);
-    float* dbg = (p.dbg && split == 0 && qi < g.H && qj < g.W)
-                     ? p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw)
-                     : nullptr;
+    for (int j = 0; j < 4; ++j) {
+      m4[j] = -INFINITY;
+      l2[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc2[j][c] = make_float2(0.f, 0.f);
+    }
+    const bool want_dump = p.dbg && split == 0;
     const int nchunks = g.nchunks, nvb = g.nvb, vt_tile = g.vt_tile;
 #ifdef CDS_PROFILE_SWITCHES
     const bool prof_pass1_only = (p.flags & 1) != 0, prof_mma_only = (p.flags & 2) != 0;   // CDS_DEBUG_FLAGS
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
-      const bool dump = (dbg != nullptr) && n == 0;
+      const bool dump = want_dump && n == 0;
       for (int ch = 0; ch < nchunks; ++ch, ++unit) {
         const int s = unit % S;
         mbar_wait(bar_vready + 8 * s, (unit / S) & 1, 4);
@@ -263,13 +268,12 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
         for (int vb = 0; vb < nvb; ++vb, ++T, vtile += vt_tile) {
           const uint32_t buf = T & 1u;
-          const float* v01 = vtile;
           mbar_wait(bar_tfull + 8 * buf, (T >> 1) & 1u, 5);
           tc_fence_after();
           uint32_t taddr = tmem_base + buf * 256 + lane_addr;
           int Nr = N;
           asm volatile("" : "+r"(taddr), "+r"(Nr));   // opaque: keep in registers instead of recomputing per chunk
-          const float* v2 = vtile + 2 * Nr;
+          const float4* vt4 = reinterpret_cast<const float4*>(vtile) + t4;   // [(chunk*C + c)*4 + t4]
           // partial blocks inside the row and rounded-up patch rows are already masked by the norm plane's marker;
           // explicit masking is only needed when an 8-column block runs past the end of the image row
           const bool edge = weak_marker || 8 * vb + 8 > g.W;
@@ -282,76 +286,103 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             continue;
           }
 #endif
+          // r[0..7]: lanes +0..15, r[8..15]: lanes +16..31; element (row j, column pair h, lo) = r[EL(j,h) + lo],
+          // its tile column = c0 + 8*h + 2*t4 + lo
+#define EL(j, h) (8 * ((j) >> 1) + 2 * ((j) & 1) + 4 * (h))
           // `slow` = tiles that need explicit column masking or the debug dump; the common path carries neither check
           auto chunk = [&](uint32_t* r, int c0, auto slow) {
             // columns that are not valid patches are forced to -FLT_MAX: they never win the max and get weight 0
             if (decltype(slow)::value && edge) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (((c0 + e) & 7) >= nval_v || ((c0 + e) >> 3) >= nval_u) r[e] = 0xff7fffffu;
-            }
-            // pass 1: best logit of the chunk (c1 > 0, so the max commutes with the affine map)
-            float dmax = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+              for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int e = 3; e < 15; e += 2) dmax = max3(dmax, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-            dmax = fmaxf(dmax, __uint_as_float(r[15]));
-            const float cmax = fmaf(dmax, c1, lw);
+                for (int lo = 0; lo < 2; ++lo)
+                  if (2 * t4 + lo >= nval_v || (c0 >> 3) + h >= nval_u) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) r[EL(j, h) + lo] = 0xff7fffffu;
+                  }
+            }
+            // pass 1: best logit per row of the chunk (c1 > 0, so the max commutes with the affine map)
+            float cm[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float d = fmaxf(max3(__uint_as_float(r[EL(j, 0)]), __uint_as_float(r[EL(j, 0) + 1]),
+                                         __uint_as_float(r[EL(j, 1)])), __uint_as_float(r[EL(j, 1) + 1]));
+              cm[j] = fmaf(d, c1, lw);
+            }
             if (decltype(slow)::value && dump) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int u = u0 + ((c0 + e) >> 3), v = 8 * vb + ((c0 + e) & 7);
-                if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[e]) * inv_scale;
+              for (int j = 0; j < 4; ++j) {
+                const int q = 32 * lq + tr + 8 * j, qi = i0 + (q >> 3), qj = j0 + (q & 7);
+                if (qi < g.H && qj < g.W) {
+                  float* dbg = p.dbg + ((size_t)b * g.H * g.W + (size_t)qi * g.W + qj) * ((size_t)g.Ph * g.Pw);
+#pragma unroll
+                  for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int lo = 0; lo < 2; ++lo) {
+                      const int u = u0 + (c0 >> 3) + h, v = 8 * vb + 2 * t4 + lo;
+                      if (u < g.Ph && v < g.Pw) dbg[u * g.Pw + v] = __uint_as_float(r[EL(j, h) + lo]) * inv_scale;
+                    }
+                }
               }
             }
-            // every weight of this chunk is < 2^-40 of the running max for all 32 queries of the warp: adding them
+            // every weight of this chunk is < 2^-40 of the running max for all rows of the warp: adding them
             // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
-            if (__all_sync(0xffffffffu, cmax < m - SKIP_LOG2)) return;
+            const bool low = cm[0] < m4[0] - SKIP_LOG2 && cm[1] < m4[1] - SKIP_LOG2 && cm[2] < m4[2] - SKIP_LOG2 &&
+                             cm[3] < m4[3] - SKIP_LOG2;
+            if (__all_sync(0xffffffffu, low)) return;
 #ifdef CDS_PROFILE_SWITCHES
-            if (prof_pass1_only) { m = fmaxf(m, cmax); return; }     // profiling: pass 1 only
-#endif
-            if (cmax > m) {                        // rare after the first few images
-              const float sc = ex2(m - cmax);
-              const float2 sc2 = make_float2(sc, sc);
-              l2 = mul2(l2, sc2);
+            if (prof_pass1_only) {     // profiling: pass 1 only
 #pragma unroll
-              for (int c = 0; c < C; ++c) acc2[c] = mul2(acc2[c], sc2);
-              m = cmax;
+              for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m4[j], cm[j]);
+              return;
+            }
+#endif
+            if (cm[0] > m4[0] || cm[1] > m4[1] || cm[2] > m4[2] || cm[3] > m4[3]) {   // rare after the first few images
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (cm[j] > m4[j]) {
+                  const float sc = ex2(m4[j] - cm[j]);
+                  const float2 sc2 = make_float2(sc, sc);
+                  l2[j] = mul2(l2[j], sc2);
+#pragma unroll
+                  for (int c = 0; c < C; ++c) acc2[j][c] = mul2(acc2[j][c], sc2);
+                  m4[j] = cm[j];
+                }
             }
             // pass 2: weights and weighted sums
-            const float off = lw - m;
-            const float2 off2 = make_float2(off, off);
-            const float* pv01 = v01 + 2 * c0;
-            const float* pv2 = v2 + c0;
+            const float4* pv = vt4 + (c0 >> 4) * (C * 4);
+            float4 v[C];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float2 ar = fma2(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), c1c1, off2);
-              const float2 w = make_float2(ex2(ar.x), ex2(ar.y));
-              l2 = add2(l2, w);
-              if (C == 1) {
-                acc2[0] = fma2(w, *reinterpret_cast<const float2*>(pv01 + 4 * e), acc2[0]);
-              } else {
-                const float4 vv = *reinterpret_cast<const float4*>(pv01 + 4 * e);
-                acc2[0] = fma2(w, make_float2(vv.x, vv.y), acc2[0]);
-                acc2[1 % C] = fma2(w, make_float2(vv.z, vv.w), acc2[1 % C]);
-                if (C > 2) acc2[2 % C] = fma2(w, *reinterpret_cast<const float2*>(pv2 + 2 * e), acc2[2 % C]);
+            for (int c = 0; c < C; ++c) v[c] = pv[c * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float off = lw - m4[j];
+              const float2 off2 = make_float2(off, off);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float2 ar = fma2(make_float2(__uint_as_float(r[EL(j, h)]), __uint_as_float(r[EL(j, h) + 1])), c1c1, off2);
+                const float2 w = make_float2(ex2(ar.x), ex2(ar.y));
+                l2[j] = add2(l2[j], w);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                  acc2[j][c] = fma2(w, h == 0 ? make_float2(v[c].x, v[c].y) : make_float2(v[c].z, v[c].w), acc2[j][c]);
               }
             }
           };
-          // software-pipelined TMEM reads: the next chunk's tcgen05.ld is in flight while this one is consumed
+#undef EL
+          // no register double-buffering of the TMEM reads: four warpgroups at 96 registers hide the tcgen05.ld latency
+          // better than three at 128 with a prefetch (171 vs 179 ms per trajectory step)
+          auto ld = [&](int c0, uint32_t* r) {
+            tmem_ld_16x256b_x2(taddr + c0, r);
+            tmem_ld_16x256b_x2(taddr + (16u << 16) + c0, r + 8);
+          };
           auto sweep = [&](auto slow) {
-            uint32_t ra[16], rb[16];
-            int c0 = 16 * wg;
-            if (c0 < Nr) tmem_ld16(taddr + c0, ra);
-            while (c0 < Nr) {
+            uint32_t ra[16];
+            for (int c0 = 16 * wg; c0 < Nr; c0 += 16 * NUM_EPI_WG) {
+              ld(c0, ra);
               tmem_ld_wait16(ra);
-              const int c1n = c0 + 16 * NUM_EPI_WG;
-              if (c1n < Nr) tmem_ld16(taddr + c1n, rb);
               chunk(ra, c0, slow);
-              if (c1n >= Nr) break;
-              tmem_ld_wait16(rb);
-              c0 = c1n + 16 * NUM_EPI_WG;
-              if (c0 < Nr) tmem_ld16(taddr + c0, ra);
-              chunk(rb, c1n, slow);
             }
           };
           if (edge || dump) sweep(std::true_type{});
@@ -364,9 +395,30 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
       }
     }
-    float l = l2.x + l2.y, acc[C];
+    // the four threads t4 = 0..3 of a row group hold the same four rows over disjoint columns: merge them with shuffles,
+    // after which thread (tr, t4) owns row tr + 8*t4 of its warp's 32
+    float m = -INFINITY, l = 0.f, acc[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = acc2[c].x + acc2[c].y;
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float M = fmaxf(m4[j], __shfl_xor_sync(0xffffffffu, m4[j], 1));
+      M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
+      const float sc = (m4[j] == -INFINITY) ? 0.f : ex2(m4[j] - M);
+      float lj = (l2[j].x + l2[j].y) * sc;
+      lj += __shfl_xor_sync(0xffffffffu, lj, 1);
+      lj += __shfl_xor_sync(0xffffffffu, lj, 2);
+      if (t4 == j) { m = M; l = lj; }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float aj = (acc2[j][c].x + acc2[j][c].y) * sc;
+        aj += __shfl_xor_sync(0xffffffffu, aj, 1);
+        aj += __shfl_xor_sync(0xffffffffu, aj, 2);
+        if (t4 == j) acc[c] = aj;
+      }
+    }
+    const int q = 32 * lq + tr + 8 * t4;   // query row = TMEM lane
+    const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
     // merge the warpgroups' partial softmax states and write this split's partials
     if (wg > 0) {
       float* dst = sMerge + ((wg - 1) * 128 + q) * (2 + C);

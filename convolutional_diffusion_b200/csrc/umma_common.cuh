@@ -36,7 +36,7 @@ struct UmmaGeom {
   int tile_pad;       // zeroed guard after each staged tile
   int np_off;         // offset of the norm plane inside a stage
   int vt_off;         // offset of the centre-pixel table inside a stage
-  int vt_tile;        // floats per tile of that table: [N/2 pairs][4] (v0,v1) + [N/2][2] (v2); PV variant: the
+  int vt_tile;        // floats per tile of that table: per 16-column chunk and channel 16 floats in fragment order; PV variant: the
                       // fp32 (tf32) UMMA operand V'^T [16 rows][N] K-major = N*64 bytes per tile
   int pv;             // 1 = geometry of the P.V (weighted sum on the tensor cores) variant
   int stage_bytes;
@@ -129,6 +129,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// 16 lanes x 16 columns: r0,r1 = (lane t/4, columns 2*(t%4)+{0,1}), r2,r3 = (lane t/4+8, same columns), r4..r7 = the
+// same rows, columns +8 (cute SM100_TMEM_LOAD_16dp256b2x fragment layout)
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 // the wait names the destination registers as in/out operands so that no use of them can be scheduled above it
 __device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
