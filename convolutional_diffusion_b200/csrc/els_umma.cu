@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   const int split = blockIdx.y, b = blockIdx.z;
   const long long n0 = p.n_sel * split / p.splits, n1 = p.n_sel * (split + 1) / p.splits;
   const int n_img = (int)(n1 - n0);
-  const int S = g.stages;
+  const int S = g.stages;   // 1 or 2: stage = unit & (S-1), phase = (unit >> (S-1)) & 1
 
   uint8_t* sA = smem;
   uint8_t* sStage = smem + g.smem_A;
@@ -130,10 +130,10 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       for (int n = 0; n < n_img; ++n) {
         const long long gi = p.idx[n0 + n];
         for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
-          const int s = unit % S, u0 = g.chunk_u0[ch];
+          const int s = unit & (S - 1), u0 = g.chunk_u0[ch];
           const uint32_t rows = (uint32_t)min(g.R, g.H - u0), nrows = (uint32_t)min(g.G, g.H - u0);
           const uint32_t cbytes = rows * g.S1, nbytes = nrows * g.S1;
-          mbar_wait(bar_empty + 8 * s, ((unit / S) & 1) ^ 1, 1);
+          mbar_wait(bar_empty + 8 * s, ((unit >> (S - 1)) & 1) ^ 1, 1);
           const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
           mbar_expect_tx(bar_full + 8 * s, g.bank_planes * g.C * cbytes + nbytes);
           for (int c = 0; c < g.C; ++c) {
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
       for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
-        const int s = unit % S;
-        mbar_wait(bar_full + 8 * s, (unit / S) & 1, 2);
+        const int s = unit & (S - 1);
+        mbar_wait(bar_full + 8 * s, (unit >> (S - 1)) & 1, 2);
         tc_fence_after();
         const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
         const uint32_t N = 8u * g.chunk_g[ch];
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
       for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
-        const int s = unit % S;
-        mbar_wait(bar_full + 8 * s, (unit / S) & 1, 6);
+        const int s = unit & (S - 1);
+        mbar_wait(bar_full + 8 * s, (unit >> (S - 1)) & 1, 6);
         const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
         float* vt = reinterpret_cast<float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
       const bool dump = want_dump && n == 0;
       for (int ch = 0; ch < nchunks; ++ch, ++unit) {
-        const int s = unit % S;
-        mbar_wait(bar_vready + 8 * s, (unit / S) & 1, 4);
+        const int s = unit & (S - 1);
+        mbar_wait(bar_vready + 8 * s, (unit >> (S - 1)) & 1, 4);
         const float* vtile = reinterpret_cast<const float*>(sStage + (size_t)s * g.stage_bytes + g.vt_off);
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
         for (int vb = 0; vb < nvb; ++vb, ++T, vtile += vt_tile) {
@@ -290,17 +290,21 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           // its tile column = c0 + 8*h + 2*t4 + lo
 #define EL(j, h) (8 * ((j) >> 1) + 2 * ((j) & 1) + 4 * (h))
           // `slow` = tiles that need explicit column masking or the debug dump; the common path carries neither check
-          auto chunk = [&](uint32_t* r, int c0, auto slow) {
-            // columns that are not valid patches are forced to -FLT_MAX: they never win the max and get weight 0
+          auto chunk = [&](uint32_t* r, int c0, const float4* pv, auto slow) {
+            // columns that are not valid patches are forced to -inf for the max and get weight 0 explicitly in pass 2
+            // (a thread may own nothing but masked columns: its state then stays (-inf, 0, 0) and drops out of the merge)
+            bool mk[2][2] = {{false, false}, {false, false}};
             if (decltype(slow)::value && edge) {
 #pragma unroll
               for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int lo = 0; lo < 2; ++lo)
-                  if (2 * t4 + lo >= nval_v || (c0 >> 3) + h >= nval_u) {
+                for (int lo = 0; lo < 2; ++lo) {
+                  mk[h][lo] = 2 * t4 + lo >= nval_v || (c0 >> 3) + h >= nval_u;
+                  if (mk[h][lo]) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) r[EL(j, h) + lo] = 0xff7fffffu;
+                    for (int j = 0; j < 4; ++j) r[EL(j, h) + lo] = 0xff800000u;
                   }
+                }
             }
             // pass 1: best logit per row of the chunk (c1 > 0, so the max commutes with the affine map)
             float cm[4];
@@ -328,9 +332,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             }
             // every weight of this chunk is < 2^-40 of the running max for all rows of the warp: adding them
             // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
-            const bool low = cm[0] < m4[0] - SKIP_LOG2 && cm[1] < m4[1] - SKIP_LOG2 && cm[2] < m4[2] - SKIP_LOG2 &&
-                             cm[3] < m4[3] - SKIP_LOG2;
-            if (__all_sync(0xffffffffu, low)) return;
+            const float lead = fmaxf(max3(cm[0] - m4[0], cm[1] - m4[1], cm[2] - m4[2]), cm[3] - m4[3]);
+            if (__all_sync(0xffffffffu, lead < -SKIP_LOG2)) return;
 #ifdef CDS_PROFILE_SWITCHES
             if (prof_pass1_only) {     // profiling: pass 1 only
 #pragma unroll
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               return;
             }
 #endif
-            if (cm[0] > m4[0] || cm[1] > m4[1] || cm[2] > m4[2] || cm[3] > m4[3]) {   // rare after the first few images
+            if (lead > 0.f) {   // some row has a new maximum: rare after the first few images
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (cm[j] > m4[j]) {
@@ -351,7 +354,6 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
                 }
             }
             // pass 2: weights and weighted sums
-            const float4* pv = vt4 + (c0 >> 4) * (C * 4);
             float4 v[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) v[c] = pv[c * 4];
@@ -362,7 +364,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const float2 ar = fma2(make_float2(__uint_as_float(r[EL(j, h)]), __uint_as_float(r[EL(j, h) + 1])), c1c1, off2);
-                const float2 w = make_float2(ex2(ar.x), ex2(ar.y));
+                float2 w = make_float2(ex2(ar.x), ex2(ar.y));
+                if (decltype(slow)::value) {
+                  if (mk[h][0]) w.x = 0.f;
+                  if (mk[h][1]) w.y = 0.f;
+                }
                 l2[j] = add2(l2[j], w);
 #pragma unroll
                 for (int c = 0; c < C; ++c)
@@ -379,10 +385,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           };
           auto sweep = [&](auto slow) {
             uint32_t ra[16];
-            for (int c0 = 16 * wg; c0 < Nr; c0 += 16 * NUM_EPI_WG) {
+            const float4* pv = vt4 + wg * (C * 4);
+            for (int c0 = 16 * wg; c0 < Nr; c0 += 16 * NUM_EPI_WG, pv += NUM_EPI_WG * C * 4) {
               ld(c0, ra);
               tmem_ld_wait16(ra);
-              chunk(ra, c0, slow);
+              chunk(ra, c0, pv, slow);
             }
           };
           if (edge || dump) sweep(std::true_type{});
