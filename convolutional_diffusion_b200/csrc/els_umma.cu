@@ -122,6 +122,27 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *sTmemBase;
 
+  // ---- resident query slices: the first n_tmem K=16 slices of the A operand are copied into TMEM once (row q = lane q,
+  // one column = two K elements), so those UMMAs stop re-reading 4 KB of shared memory per candidate tile
+  if (g.n_tmem > 0) {
+    if (warp >= 4 && warp < 8) {
+      const int q = tid - 128;
+      const uint8_t* rowp = sA + (size_t)(q >> 3) * g.RA + (size_t)(q & 7) * 16;
+      const uint32_t dst = tmem_base + g.a_tmem_col + (((uint32_t)((warp & 3) * 32)) << 16);
+      for (int t = 0; t < g.n_tmem; ++t) {
+        const uint32_t ex = p.table[t].x;
+        const uint4 k0 = *reinterpret_cast<const uint4*>(rowp + ((ex & 0x3FFFu) << 4));
+        const uint4 k1 = *reinterpret_cast<const uint4*>(rowp + ((ex & 0x3FFFu) << 4) + (((ex >> 16) & 0x3FFFu) << 4));
+        const uint32_t v[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+        tmem_st8(dst + 8 * t, v);
+      }
+      tmem_st_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
   if (warp == 0) {
     // =========================== producer: per (image, band) unit one bulk copy per channel (+ residual plane) of the
     // band's strip rows, and one of its norm-plane rows
@@ -152,7 +173,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     // runs on the uniform datapath.
     const uint64_t a_hi = desc_hi(g.RA), b_hi = desc_hi(g.S1);
     const uint32_t a_base = smem_u32(sA) >> 4;
-    const int nm = g.n_mma;
+    const int nm = g.n_mma, nt = g.n_tmem;
+    const uint32_t a_tmem = tmem_base + g.a_tmem_col;
     long long T = 0;
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
@@ -169,17 +191,17 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           const int buf = (int)(T & 1);
           mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((T >> 1) & 1) ^ 1), 3);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * 256;
+          const uint32_t d_tmem = tmem_base + buf * g.tmem_buf1;
           const uint32_t b_base = (stage_addr + vb * 128u) >> 4;      // band-relative: patch row u0 is strip row 0
           if (elect_one()) {
-            {
-              const uint2 e = p.table[0];
-              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 0u);
-            }
+            int t = 0;
 #pragma unroll 4
-            for (int t = 1; t < nm; ++t) {
+            for (; t < nt; ++t)       // query slice resident in TMEM
+              umma_f16_ts(d_tmem, a_tmem + 8 * t, b_hi | (uint64_t)(p.table[t].y + b_base), idesc, t ? 1u : 0u);
+#pragma unroll 4
+            for (; t < nm; ++t) {     // query slice read from shared memory
               const uint2 e = p.table[t];
-              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, 1u);
+              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, t ? 1u : 0u);
             }
             umma_commit(bar_tfull + 8 * buf);
           }
@@ -270,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           const uint32_t buf = T & 1u;
           mbar_wait(bar_tfull + 8 * buf, (T >> 1) & 1u, 5);
           tc_fence_after();
-          uint32_t taddr = tmem_base + buf * 256 + lane_addr;
+          uint32_t taddr = tmem_base + buf * g.tmem_buf1 + lane_addr;
           int Nr = N;
           asm volatile("" : "+r"(taddr), "+r"(Nr));   // opaque: keep in registers instead of recomputing per chunk
           const float4* vt4 = reinterpret_cast<const float4*>(vtile) + t4;   // [(chunk*C + c)*4 + t4]
@@ -542,6 +564,8 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
   {
     const char* f = getenv("CDS_DEBUG_FLAGS");
     p.flags = f ? atoi(f) : 0;
+    const char* at = getenv("CDS_A_TMEM");     // A/B switch: 0 = every query slice from shared memory
+    if (at && atoi(at) == 0) p.g.n_tmem = 0;
   }
   const int tiles = ((H + TI - 1) / TI) * ((W + TJ - 1) / TJ);
   dim3 grid(tiles, splits, B);

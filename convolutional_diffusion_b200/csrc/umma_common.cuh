@@ -44,6 +44,9 @@ struct UmmaGeom {
   int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
   int nvb;            // 8-column blocks of candidate patches
   int n_mma;          // descriptor-table entries per accumulator tile (all precision combinations)
+  int tmem_buf1;      // TMEM column of the second accumulator buffer (the first sits at column 0)
+  int a_tmem_col;     // TMEM column of the resident query K slices (8 columns = one K=16 slice of all 128 rows)
+  int n_tmem;         // the first n_tmem table entries take their A operand from TMEM instead of shared memory
   int passes, bank_planes;
   int smem_A, smem_stage, smem_merge, smem_table, smem_bar, smem_total;
 };
@@ -119,6 +122,19 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
 }
+// same with the A operand resident in TMEM (lane = row, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -295,6 +311,12 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
     if (nm < 0) return 0;
   }
   g.n_mma = nm;
+  // TMEM: two accumulator buffers of 8*G columns; what is left holds query K slices, which the tensor core then reads
+  // from TMEM instead of re-reading them from shared memory for every candidate tile
+  g.tmem_buf1 = pv ? 256 : 8 * g.G;
+  g.a_tmem_col = 2 * g.tmem_buf1;
+  g.n_tmem = pv ? 0 : (TMEM_COLS - g.a_tmem_col) / 8;
+  if (g.n_tmem > nm) g.n_tmem = nm;
   g.smem_stage = g.stages * g.stage_bytes;
   g.smem_total = fixed + g.smem_stage;
   return g.smem_total <= 227 * 1024;
