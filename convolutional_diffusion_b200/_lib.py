@@ -32,7 +32,7 @@ SIGNATURES = {
     "cds_ls_rows_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_bbels_edge_supported": (_i, [_i, _i, _i, _i]),
     "cds_bbels_edge_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
-    "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,
+    "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,
                                    _p, _p, _p, _p, _p]),
     "cds_els_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
     "cds_els_partials_umma_pv": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,

@@ -62,6 +62,7 @@ class PatchBank:
         self.N, self.C, self.H, self.W = self.images.shape
         assert self.labels.shape[0] == self.N
         self._strip = None
+        self._rows8 = None
         self._pnorm = {}
         self._nplane = {}
         self._sel = {}
@@ -86,6 +87,20 @@ class PatchBank:
                                                         scale, 1, _lib.ptr(lo), _lib.stream_ptr()), "cds_pack_strip8")
                 self._strip = (hi, lo, scale)
         return self._strip
+
+    def rows8(self):
+        """fp16 plane of 8-pixel HORIZONTAL strips (same scale as strip8), or None for a two-plane bank: lets the
+        tensor-core kernel contract the trailing k % 8 patch rows without padding them to a block of 8."""
+        hi, lo, scale = self.strip8()
+        if lo is not None:
+            return None
+        if self._rows8 is None:
+            with torch.cuda.device(self.device):
+                out = torch.empty(self.N * self.C * self.H * self.W * 8, dtype=torch.float16, device=self.device)
+                _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
+                                                    scale, 2, _lib.ptr(out), _lib.stream_ptr()), "cds_pack_strip8")
+                self._rows8 = out
+        return self._rows8
 
     def patch_norms(self, k):
         """||p||^2 of every valid k x k x C patch, [N, (H-k+1)*(W-k+1)] fp32 (computed once per k)."""

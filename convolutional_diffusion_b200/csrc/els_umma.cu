@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   // zero the staging area once: guard pads behind the tiles and band rows past the image bottom are never written by
   // the bulk copies, and whatever masked columns / zero-weighted K slots read there must stay finite
   for (int e = tid * 16; e < g.smem_stage; e += THREADS * 16) *reinterpret_cast<uint4*>(sStage + e) = make_uint4(0, 0, 0, 0);
+  if (g.rem) __syncthreads();     // the horizontal query regions below are built inside the zeroed staging area
   {
     // A[plane][c][blk][gi][jj][8]: element e of granule (gi,jj) of block blk = xpad[i0+gi+8*blk+e][j0+jj] (patch
     // coordinates: padded row = pixel row + dy, i.e. source pixel row i0+gi+dy-d), zero where dy = 8*blk+e >= k
@@ -103,6 +104,33 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<uint4*>(hi);
       if (g.passes > 1) *reinterpret_cast<uint4*>(sA + g.a_plane + off) = *reinterpret_cast<uint4*>(lo);
     }
+    // mixed K layout: patch rows dy = 8*nb + r (r < rem) as horizontal granules; region (c,r,blk)[gi][jj][8], element e of
+    // granule (gi,jj) = xpad[i0+gi+dy][j0+jj+8*blk+e], zero where dx = 8*blk+e >= k.  Scratch copy in the staging area:
+    // these slices go to TMEM below and are never read from shared memory by a UMMA
+    const int per_h = C * g.rem * g.nbh * TI * 8;
+    for (int e = tid; e < per_h; e += THREADS) {
+      const int jj = e & 7, gi = (e >> 3) % TI, blk = (e / (8 * TI)) % g.nbh, r = (e / (8 * TI * g.nbh)) % g.rem,
+                c = e / (8 * TI * g.nbh * g.rem);
+      __half hi[8], lo[8];
+      int yr = i0 + gi + 8 * g.nb + r - g.d;
+      bool rowok = true;
+      if (p.pad == CDS_PAD_CIRCULAR) yr = ((yr % g.H) + g.H) % g.H;
+      else rowok = (yr >= 0 && yr < g.H);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int dx = 8 * blk + q;
+        int xc = j0 + jj + dx - g.d;
+        bool ok = rowok && dx < g.k;
+        if (p.pad == CDS_PAD_CIRCULAR) xc = ((xc % g.W) + g.W) % g.W;
+        else ok = ok && (xc >= 0 && xc < g.W);
+        const float v = ok ? xb[(c * g.H + yr) * g.W + xc] : 0.f;
+        hi[q] = __float2half_rn(v);
+        lo[q] = __float2half_rn(v - __half2float(hi[q]));
+      }
+      const size_t off = (size_t)((c * g.rem + r) * g.nbh + blk) * (TI * 128) + (size_t)gi * 128 + (size_t)jj * 16;
+      *reinterpret_cast<uint4*>(sStage + off) = *reinterpret_cast<uint4*>(hi);
+      if (g.passes > 1) *reinterpret_cast<uint4*>(sStage + g.h_plane + off) = *reinterpret_cast<uint4*>(lo);
+    }
     // constant block: every granule = three-way fp16 split of gamma = -a*scale/2, laid out against the norm plane's
     // (ph, pm, pl, ph, pm, ph, 0, 0) so that the K sum is (gh+gm+gl)*(ph+pm+pl) up to terms below 2^-30
     const float gamma = -0.5f * a * p.scale;
@@ -127,10 +155,10 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   if (g.n_tmem > 0) {
     if (warp >= 4 && warp < 8) {
       const int q = tid - 128;
-      const uint8_t* rowp = sA + (size_t)(q >> 3) * g.RA + (size_t)(q & 7) * 16;
       const uint32_t dst = tmem_base + g.a_tmem_col + (((uint32_t)((warp & 3) * 32)) << 16);
       for (int t = 0; t < g.n_tmem; ++t) {
         const uint32_t ex = p.table[t].x;
+        const uint8_t* rowp = ((ex >> 31) ? sStage + (size_t)(q >> 3) * 128 : sA + (size_t)(q >> 3) * g.RA) + (size_t)(q & 7) * 16;
         const uint4 k0 = *reinterpret_cast<const uint4*>(rowp + ((ex & 0x3FFFu) << 4));
         const uint4 k1 = *reinterpret_cast<const uint4*>(rowp + ((ex & 0x3FFFu) << 4) + (((ex >> 16) & 0x3FFFu) << 4));
         const uint32_t v[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
@@ -141,6 +169,12 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (g.rem) {      // give the scratch region back to the pipeline as zeros
+      for (int e = tid * 16; e < g.passes * g.h_plane; e += THREADS * 16)
+        *reinterpret_cast<uint4*>(sStage + e) = make_uint4(0, 0, 0, 0);
+      fence_proxy_async();
+      __syncthreads();
+    }
   }
 
   if (warp == 0) {
@@ -156,12 +190,17 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           const uint32_t cbytes = rows * g.S1, nbytes = nrows * g.S1;
           mbar_wait(bar_empty + 8 * s, ((unit >> (S - 1)) & 1) ^ 1, 1);
           const uint32_t dst = smem_u32(sStage + (size_t)s * g.stage_bytes);
-          mbar_expect_tx(bar_full + 8 * s, g.bank_planes * g.C * cbytes + nbytes);
+          const uint32_t hrow0 = (uint32_t)(u0 + 8 * g.nb);
+          const uint32_t hbytes = g.rem ? (uint32_t)min(g.Rh, g.H - (int)hrow0) * g.S1 : 0u;
+          mbar_expect_tx(bar_full + 8 * s, g.bank_planes * g.C * cbytes + g.C * hbytes + nbytes);
           for (int c = 0; c < g.C; ++c) {
             const size_t src = ((size_t)gi * g.C + c) * g.chan_bytes + (size_t)u0 * g.S1;
             bulk_g2s(dst + c * g.R * g.S1, p.bank_hi + src, cbytes, bar_full + 8 * s);
             if (g.bank_planes > 1)
               bulk_g2s(dst + g.img_bytes + g.tile_pad + c * g.R * g.S1, p.bank_lo + src, cbytes, bar_full + 8 * s);
+            if (g.rem)
+              bulk_g2s(dst + g.hb_off + c * g.Rh * g.S1, p.bank_rows + ((size_t)gi * g.C + c) * g.chan_bytes + (size_t)hrow0 * g.S1,
+                       hbytes, bar_full + 8 * s);
           }
           bulk_g2s(dst + g.np_off, p.norm_plane + (size_t)gi * g.chan_bytes + (size_t)u0 * g.S1, nbytes, bar_full + 8 * s);
         }
@@ -193,6 +232,13 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * g.tmem_buf1;
           const uint32_t b_base = (stage_addr + vb * 128u) >> 4;      // band-relative: patch row u0 is strip row 0
+#ifdef CDS_PROFILE_SWITCHES
+          if (p.flags & 8) {       // profiling: epilogue only (no UMMAs issued, accumulators keep whatever they held)
+            if (elect_one()) umma_commit(bar_tfull + 8 * buf);
+            __syncwarp();
+            continue;
+          }
+#endif
           if (elect_one()) {
             int t = 0;
 #pragma unroll 4
@@ -273,7 +319,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 #pragma unroll
       for (int c = 0; c < C; ++c) acc2[j][c] = make_float2(0.f, 0.f);
     }
-    const bool want_dump = p.dbg && split == 0;
+    int want_dump = (p.dbg && split == 0) ? 1 : 0;
+    uint32_t bar_t = bar_tfull;     // tfull at +0/+8, tempty at +16/+24
+    asm volatile("" : "+r"(bar_t), "+r"(want_dump));   // opaque: one register each instead of per-tile recomputation
     const int nchunks = g.nchunks, nvb = g.nvb, vt_tile = g.vt_tile;
 #ifdef CDS_PROFILE_SWITCHES
     const bool prof_pass1_only = (p.flags & 1) != 0, prof_mma_only = (p.flags & 2) != 0;   // CDS_DEBUG_FLAGS
@@ -282,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
       const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
-      const bool dump = want_dump && n == 0;
+      const bool dump = want_dump != 0 && n == 0;
       for (int ch = 0; ch < nchunks; ++ch, ++unit) {
         const int s = unit & (S - 1);
         mbar_wait(bar_vready + 8 * s, (unit >> (S - 1)) & 1, 4);
@@ -290,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         const int N = 8 * g.chunk_g[ch], u0 = g.chunk_u0[ch];
         for (int vb = 0; vb < nvb; ++vb, ++T, vtile += vt_tile) {
           const uint32_t buf = T & 1u;
-          mbar_wait(bar_tfull + 8 * buf, (T >> 1) & 1u, 5);
+          mbar_wait(bar_t + 8 * buf, (T >> 1) & 1u, 5);
           tc_fence_after();
           uint32_t taddr = tmem_base + buf * g.tmem_buf1 + lane_addr;
           int Nr = N;
@@ -407,8 +455,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           };
           auto sweep = [&](auto slow) {
             uint32_t ra[16];
-            const float4* pv = vt4 + wg * (C * 4);
-            for (int c0 = 16 * wg; c0 < Nr; c0 += 16 * NUM_EPI_WG, pv += NUM_EPI_WG * C * 4) {
+            // chunk i of tile T goes to warpgroup (i + T * chunks_per_tile) mod NUM_EPI_WG: the warpgroup that gets the
+            // extra chunk of an uneven tile rotates, and the two TMEM buffers let the others run one tile ahead
+            const int first = (int)((uint32_t)(wg + NUM_EPI_WG * 64 - (int)((T * (uint32_t)(Nr >> 4)) % NUM_EPI_WG)) % NUM_EPI_WG);
+            const float4* pv = vt4 + first * (C * 4);
+            for (int c0 = 16 * first; c0 < Nr; c0 += 16 * NUM_EPI_WG, pv += NUM_EPI_WG * C * 4) {
               ld(c0, ra);
               tmem_ld_wait16(ra);
               chunk(ra, c0, pv, slow);
@@ -418,10 +469,10 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           else sweep(std::false_type{});
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          if (elect_one()) mbar_arrive(bar_t + 16 + 8 * buf);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        if (elect_one()) mbar_arrive(bar_empty + 8 * s);
       }
     }
     // the four threads t4 = 0..3 of a row group hold the same four rows over disjoint columns: merge them with shuffles,
@@ -542,21 +593,41 @@ extern "C" int cds_pack_norm_plane(const float* images, int64_t N, int C, int H,
 }
 
 extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
-                                     const void* bank_hi, const void* bank_lo, float bank_scale, const void* norm_plane,
-                                     const int32_t* idx, const float* logw, int64_t n_sel, int splits, int passes,
-                                     float* m, float* l, float* acc, float* dbg_dots, void* stream) {
+                                     const void* bank_hi, const void* bank_lo, const void* bank_rows, float bank_scale,
+                                     const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
+                                     int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
+                                     void* stream) {
   UmmaParams p;
   const int planes = bank_lo ? 2 : 1;
-  if (!make_geom(C, H, W, k, passes, planes, p.g, p.table)) {
+  // with a rows8 plane the trailing k % 8 patch rows are contracted as horizontal granules (fewer, fuller UMMAs);
+  // geometries that layout does not cover fall back to vertical granules only
+  const char* mx = getenv("CDS_ELS_MIXED");     // A/B switch: 0 = vertical granules only
+  const bool try_mixed = bank_rows != nullptr && !(mx && atoi(mx) == 0);
+  bool have = false;
+  if (try_mixed) {
+    UmmaGeom gv;
+    static thread_local uint2 scratch[MAX_MMAS];
+    const bool okv = make_geom(C, H, W, k, passes, planes, gv, scratch) != 0;
+    const bool okm = make_geom(C, H, W, k, passes, planes, p.g, p.table, 0, 1) != 0;
+    // the mixed layout must keep the tiling (same band height and staging depth: the epilogue cost per image is then
+    // unchanged) and save at least 8 % of the UMMAs.  Measured on 32x32x3: k=17 8.5 -> 6.5 ms; k=9 with the band
+    // halved to fit shared memory was 12 % slower although it issues 39 % fewer UMMAs (epilogue bound).
+    have = okm && (!okv || (p.g.stages >= gv.stages && p.g.G == gv.G && p.g.n_mma * 100 < gv.n_mma * 92));
+  }
+  if (!have && !make_geom(C, H, W, k, passes, planes, p.g, p.table)) {
     cds_set_error("cds_els_partials_umma: unsupported geometry C=%d H=%d W=%d k=%d passes=%d planes=%d", C, H, W, k,
                   passes, planes);
     return CDS_ERR_UNSUPPORTED;
   }
+  if (getenv("CDS_DEBUG_GEOM"))
+    fprintf(stderr, "cdscore: els_umma k=%d passes=%d planes=%d mixed=%d G=%d chunks=%d nvb=%d n_mma=%d n_tmem=%d stages=%d smem=%d\n",
+            k, passes, planes, p.g.rem ? 1 : 0, p.g.G, p.g.nchunks, p.g.nvb, p.g.n_mma, p.g.n_tmem, p.g.stages, p.g.smem_total);
   CDS_CHECK_ARG(B >= 1 && n_sel >= 1 && splits >= 1, "cds_els_partials_umma: empty problem");
   if (splits > n_sel) splits = (int)n_sel;
   p.B = B; p.pad = query_pad; p.splits = splits; p.n_sel = n_sel;
   p.x = x; p.beta = beta;
   p.bank_hi = (const uint8_t*)bank_hi; p.bank_lo = (const uint8_t*)bank_lo;
+  p.bank_rows = (const uint8_t*)bank_rows;
   p.norm_plane = (const uint8_t*)norm_plane;
   p.scale = bank_scale;
   p.idx = idx; p.logw = logw;

@@ -457,6 +457,7 @@ extern "C" int cds_els_partials_umma_pv(int query_pad, const float* x, int B, in
   p.B = B; p.pad = query_pad; p.splits = splits; p.n_sel = n_sel;
   p.x = x; p.beta = beta;
   p.bank_hi = (const uint8_t*)bank_hi; p.bank_lo = (const uint8_t*)bank_lo;
+  p.bank_rows = nullptr;
   p.norm_plane = (const uint8_t*)norm_plane;
   p.scale = bank_scale;
   p.idx = idx; p.logw = logw;

@@ -130,9 +130,11 @@ __global__ void pack_strip8_kernel(const float* __restrict__ images, long long N
     __half h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float v = (u + e < H) ? src[(u + e) * W + xx] * scale : 0.f;
+      float v;
+      if (plane == 2) v = (xx + e < W) ? src[u * W + xx + e] * scale : 0.f;     // rows8: horizontal strip
+      else v = (u + e < H) ? src[(u + e) * W + xx] * scale : 0.f;
       __half hi = __float2half_rn(v);
-      h[e] = plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
+      h[e] = plane == 1 ? __float2half_rn(v - __half2float(hi)) : hi;
     }
     out[g] = *reinterpret_cast<uint4*>(h);
   }

@@ -44,6 +44,13 @@ struct UmmaGeom {
   int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
   int nvb;            // 8-column blocks of candidate patches
   int n_mma;          // descriptor-table entries per accumulator tile (all precision combinations)
+  int rem, nbh;       // mixed K layout: the last rem = k - 8*nb patch rows are contracted as nbh horizontal 8-pixel granules
+                      // per row ("rows8" bank plane) instead of one more mostly-empty vertical block; rem = 0: off
+  int h_plane;        // the horizontal query regions are TMEM resident; they are built once in the (not yet used) staging
+                      // area: region (plane,c,r,blk) = TI*128 bytes at plane*h_plane + ..., followed by TI*128 zero bytes
+  int n_h;            // table entries (always the first ones) that contract horizontal granules
+  int Rh;             // rows of the rows8 band staged per channel = G + rem - 1
+  int hb_off;         // offset of that band inside a stage
   int tmem_buf1;      // TMEM column of the second accumulator buffer (the first sits at column 0)
   int a_tmem_col;     // TMEM column of the resident query K slices (8 columns = one K=16 slice of all 128 rows)
   int n_tmem;         // the first n_tmem table entries take their A operand from TMEM instead of shared memory
@@ -59,6 +66,7 @@ struct UmmaParams {
   const float* beta;
   const uint8_t* bank_hi;
   const uint8_t* bank_lo;
+  const uint8_t* bank_rows;   // rows8 plane (horizontal granules) or null
   const uint8_t* norm_plane;
   float scale;
   const int32_t* idx;
@@ -233,15 +241,22 @@ inline int emit_pairs(const Gran* gr, int n, int a_zero, uint2* table, int nm) {
   return nm;
 }
 
-inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom& g, uint2* table, int pv = 0) {
+// mixed = 1: contract the patch rows beyond the last full block of 8 through the rows8 plane (needs k > 8, k % 8 != 0,
+// a single-plane bank); returns 0 when that layout does not apply or does not fit
+inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, UmmaGeom& g, uint2* table, int pv = 0,
+                     int mixed = 0) {
   if (C < 1 || C > 3 || H > 64 || W > 64 || H < k || W < k || (k & 1) == 0 || k < 3) return 0;
   if (passes < 1 || passes > 2 || bank_planes < 1 || bank_planes > 2) return 0;
+  if (mixed && (pv || bank_planes > 1 || k < 9 || (k & 7) == 0)) return 0;
   g.C = C; g.H = H; g.W = W; g.k = k; g.d = k / 2;
   g.Ph = H - k + 1; g.Pw = W - k + 1;
-  g.nb = (k + 7) / 8;
+  g.nb = mixed ? k / 8 : (k + 7) / 8;
+  g.rem = mixed ? k - 8 * g.nb : 0;
+  g.nbh = mixed ? (k + 7) / 8 : 0;
   g.RA = (k + 7) * 16;
   g.a_block = TI * g.RA;
   g.a_plane = C * g.nb * g.a_block;
+  g.h_plane = C * g.rem * g.nbh * TI * 128;
   g.a_const = passes * g.a_plane;
   g.a_zero = g.a_const + g.a_block;
   g.a_bytes = g.a_zero + g.a_block;
@@ -255,7 +270,7 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.smem_merge = ((NUM_EPI_WG - 1) * 128 * 5 * 4 + 127) / 128 * 128;
   g.smem_bar = 8 * 10 + 16 + 32;
   const int n_gran = C * g.nb * k;
-  const int nm_max = (passes + bank_planes - 1) * ((n_gran + 2) / 2);
+  const int nm_max = (passes + bank_planes - 1) * ((n_gran + 2) / 2 + (C * g.rem * g.nbh + 1) / 2);
   if (nm_max > MAX_MMAS) return 0;
   g.smem_table = 128;
   const int fixed = g.smem_A + g.smem_merge + g.smem_table + g.smem_bar + 1024;
@@ -265,7 +280,7 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   // the norm plane and the centre-pixel tables of its nvb tiles.  N = 8*G <= 256 candidates per UMMA, G even
   // (UMMA M=128 needs N % 16 == 0).  Pick the largest G that leaves room for two stages.
   const int halo = 8 * (g.nb - 1) > g.d ? 8 * (g.nb - 1) : g.d;
-  int bestG = 0, bestStages = 0;
+  int bestG = 0, bestStages = 0, bestWaste = 1 << 30;
   for (int G = 32; G >= 2; G -= 2) {
     if (G > ((g.Ph + 1) & ~1)) continue;
     const int nch = (g.Ph + G - 1) / G;
@@ -273,28 +288,52 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
     if (pv && 8 * G > 192) continue;                        // P.V variant: two S buffers + 2 x 4 O tiles of 16 columns in TMEM
     const int R = G + halo;
     const int band = C * R * g.S1;
+    const int hband = g.rem ? C * (G + g.rem - 1) * g.S1 + g.tile_pad : 0;
     const int vt_tile = pv ? 8 * G * 16 : 8 * G / 2 * 6;
-    const int stage = (bank_planes * (band + g.tile_pad) + G * g.S1 + g.tile_pad + g.nvb * vt_tile * 4 + 127) / 128 * 128;
+    const int stage = (bank_planes * (band + g.tile_pad) + hband + G * g.S1 + g.tile_pad + g.nvb * vt_tile * 4 + 127) / 128 * 128;
     const int st = fixed + 2 * stage <= 227 * 1024 ? 2 : (fixed + stage <= 227 * 1024 ? 1 : 0);
-    if (st > bestStages) { bestStages = st; bestG = G; }
-    if (st == 2) break;
+    // prefer two stages, then the cheapest tiling: candidate columns per image incl. padded patch rows, plus a fixed
+    // per-tile overhead worth ~32 columns (barrier round trips, pipeline fill)
+    const int waste = nch * (8 * G + 32);
+    if (st > bestStages || (st == bestStages && st > 0 && waste < bestWaste)) { bestStages = st; bestG = G; bestWaste = waste; }
   }
   if (bestG == 0) return 0;
   if (pv && bestStages < 2) return 0;                        // the P.V pipeline releases a stage two tiles late
   g.G = bestG; g.R = bestG + halo;
+  g.Rh = g.rem ? bestG + g.rem - 1 : 0;
   g.nchunks = (g.Ph + g.G - 1) / g.G;
   for (int c = 0; c < g.nchunks; ++c) { g.chunk_u0[c] = c * g.G; g.chunk_g[c] = g.G; }
   g.img_bytes = C * g.R * g.S1;                              // one precision plane of a band in shared memory
   g.np_bytes = g.G * g.S1;
-  g.np_off = bank_planes * (g.img_bytes + g.tile_pad);
+  g.hb_off = bank_planes * (g.img_bytes + g.tile_pad);
+  g.np_off = g.hb_off + (g.rem ? C * g.Rh * g.S1 + g.tile_pad : 0);
   g.vt_off = g.np_off + g.np_bytes + g.tile_pad;
   g.vt_tile = pv ? 8 * g.G * 16 : 8 * g.G / 2 * 6;          // floats per tile (see UmmaGeom::vt_tile)
   g.stage_bytes = (g.vt_off + g.nvb * g.vt_tile * 4 + 127) / 128 * 128;
   g.stages = bestStages;
 
-  // K granule lists per precision combination (query plane, bank plane): (0,0)+norm granule [, (1,0)] [, (0,1)]
+  // K granule lists.  Mixed layout first: the horizontal granules of every query plane (table.x bit 31: the A operand
+  // of these entries exists only in TMEM, built from a scratch copy with 128-byte row groups), then per precision
+  // combination (query plane, bank plane): (0,0)+norm granule [, (1,0)] [, (0,1)]
   Gran gr[3 * 4 * 32 + 2];
   int nm = 0;
+  if (g.rem) {
+    for (int pa = 0; pa < passes; ++pa) {
+      int n = 0;
+      for (int c = 0; c < C; ++c)
+        for (int r = 0; r < g.rem; ++r)
+          for (int blk = 0; blk < g.nbh; ++blk) {
+            gr[n].a = pa * g.h_plane + ((c * g.rem + r) * g.nbh + blk) * TI * 128;
+            gr[n].b = g.hb_off + ((c * g.Rh + r) * W + 8 * blk) * 16;
+            ++n;
+          }
+      nm = emit_pairs(gr, n, passes * g.h_plane, table, nm);
+      if (nm < 0) return 0;
+    }
+    for (int t = 0; t < nm; ++t) table[t].x |= 0x80000000u;
+    if (passes * g.h_plane + TI * 128 > g.stages * g.stage_bytes) return 0;
+  }
+  g.n_h = nm;
   for (int cb = 0; cb < passes + bank_planes - 1; ++cb) {
     const int pa = (cb == 1 && passes > 1) ? 1 : 0;
     const int pb = (cb > 0 && !pa) ? 1 : 0;
@@ -317,6 +356,7 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.a_tmem_col = 2 * g.tmem_buf1;
   g.n_tmem = pv ? 0 : (TMEM_COLS - g.a_tmem_col) / 8;
   if (g.n_tmem > nm) g.n_tmem = nm;
+  if (g.n_tmem < g.n_h) return 0;                            // the horizontal slices have no shared-memory copy
   g.smem_stage = g.stages * g.stage_bytes;
   g.smem_total = fixed + g.smem_stage;
   return g.smem_total <= 227 * 1024;

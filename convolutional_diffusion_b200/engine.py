@@ -177,14 +177,14 @@ class ScoreEngine:
         S = self._splits(tiles, B, n_sel)
         P = self._partials(tag, S, B)
         planes = 1 if lo is None else 2
-        fn = self.lib.cds_els_partials_umma
+        tail = (_lib.ptr(pn), _lib.ptr(idx), _lib.ptr(logw), n_sel, S, passes, _lib.ptr(P.m), _lib.ptr(P.l),
+                _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr())
+        head = (_lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(hi), _lib.ptr(lo))
         if self.els_variant == "pv" and self.lib.cds_els_umma_pv_smem_bytes(b.C, b.H, b.W, k, passes, planes) > 0:
-            fn = self.lib.cds_els_partials_umma_pv
-        _lib.check(fn(_lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta),
-                                                  _lib.ptr(hi), _lib.ptr(lo), scale, _lib.ptr(pn), _lib.ptr(idx),
-                                                  _lib.ptr(logw), n_sel, S, passes, _lib.ptr(P.m), _lib.ptr(P.l),
-                                                  _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr()),
-                   "cds_els_partials_umma")
+            _lib.check(self.lib.cds_els_partials_umma_pv(*head, scale, *tail), "cds_els_partials_umma_pv")
+        else:
+            rows = b.rows8() if (k > 8 and k % 8) else None        # mixed K layout for the trailing k % 8 patch rows
+            _lib.check(self.lib.cds_els_partials_umma(*head, _lib.ptr(rows), scale, *tail), "cds_els_partials_umma")
         self.launches += 1
         return P
 

@@ -43,7 +43,9 @@ int         cds_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   out[n][c][u][x][8] (fp16), element e = scale * img[n][c][u+e][x]  (0 beyond the last row).
  * One 16-byte granule = an 8-pixel vertical strip, so a k x k patch row block is addressable with
  * 16-byte-stride UMMA descriptors (implicit im2col; patches are never materialised).
- * plane = 0: fp16(scale*v);  plane = 1: fp16 of the rounding residual (second plane for non-8-bit banks). */
+ * plane = 0: fp16(scale*v);  plane = 1: fp16 of the rounding residual (second plane for non-8-bit banks);
+ * plane = 2: "rows8", the same values as 8-pixel HORIZONTAL strips, element e = scale * img[n][c][u][x+e]
+ * (0 beyond the last column), for the mixed K layout of cds_els_partials_umma. */
 int cds_pack_strip8(const float* images, int64_t N, int C, int H, int W, float scale, int plane,
                     void* out_f16, void* stream);
 
@@ -93,13 +95,15 @@ int cds_bbels_edge_partials(const float* x, int B, int C, int H, int W, int k, c
 /* tcgen05 / TMEM evaluation of ELS (and the bbELS centre region): queries = all H*W pixels of x padded
  * per query_pad, candidates = every valid k x k patch of the selected images, streamed from the strip8
  * bank by bulk-async copies.  passes = 1: fp16 query; 2: fp16 hi+lo query (fp32-grade dot products for
- * 8-bit banks).  bank_lo may be NULL (8-bit-exact bank).  dbg_dots: optional [B][H*W][P] raw dot dump of the
- * first selected image (tests only, may be NULL). */
+ * 8-bit banks).  bank_lo may be NULL (8-bit-exact bank).  bank_rows may be NULL; when given (the plane = 2 output of
+ * cds_pack_strip8: 8-pixel HORIZONTAL strips) and k > 8, k % 8 != 0, the trailing k % 8 patch rows are contracted
+ * as horizontal granules instead of one more mostly-empty block of 8 rows (k = 9: 17 UMMAs per tile instead of 28).
+ * dbg_dots: optional [B][H*W][P] raw dot dump of the first selected image (tests only, may be NULL). */
 int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k,
-                          const float* beta, const void* bank_hi, const void* bank_lo, float bank_scale,
-                          const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
-                          int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
-                          void* stream);
+                          const float* beta, const void* bank_hi, const void* bank_lo, const void* bank_rows,
+                          float bank_scale, const void* norm_plane, const int32_t* idx, const float* logw,
+                          int64_t n_sel, int splits, int passes, float* m, float* l, float* acc,
+                          float* dbg_dots, void* stream);
 /* Same contract, "P.V" variant: the weighted sum of the centre pixels also runs on the tensor cores (P is written
  * back to TMEM as fp16 and contracted with the per-tile value operand by a second UMMA).  Needs N <= 240 candidates
  * per accumulator tile and two shared-memory stages; cds_els_umma_pv_smem_bytes() == 0 means use the variant above. */
