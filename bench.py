@@ -263,9 +263,10 @@ def run_ours(args, scales):
         roof = {"bound": "tensor", "kernel": "els_umma_kernel", "achieved": achieved, "peak": peaks["bf16"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "frac_sustained": achieved / peaks["bf16_sustained"],
                 "peak_source": peaks["source"],
-                # DRAM bytes per launch of this kernel (ncu --set full, profiles/r01d_els_umma_ncu_summary.md: dram read+write
-                # at batch 4, class 0); algorithmic = class sub-bank strip8 + norm plane once = 324 MB
-                "traffic": 671.0e6, "traffic_algorithmic": 324.0e6,
+                # DRAM bytes per launch of this kernel (ncu --set full, profiles/r01g_els_umma_ncu_summary.md: dram read+write
+                # at batch 4, class 0, k=17: 712 MB; k=5: 621 MB, k=11: 917 MB); algorithmic = class sub-bank strip8 + norm
+                # plane + the rows8 rows of the mixed K layout once = 446 MB at k=17 (324 MB at k <= 7)
+                "traffic": 712.0e6, "traffic_algorithmic": 446.0e6,
                 "note": "algorithmic 2*k*k*C FLOP per (query, patch) pair, FLOP-weighted over the 19 evaluations of one "
                         "trajectory; CUDA events around the kernel launches on the launching stream", "per_k": per_k}
 

@@ -135,6 +135,29 @@ def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs, variant):
         assert np.max(np.abs(mu - mu_o)) < MU_TOL, (b, np.max(np.abs(mu - mu_o)))
 
 
+@pytest.mark.parametrize("precision", ["f16", "f16x2"])
+@pytest.mark.parametrize("C,H,k,t", [(3, 32, 9, 0.55), (3, 32, 11, 0.65), (3, 32, 13, 0.75), (3, 32, 17, 0.9),
+                                     (3, 32, 19, 0.9), (1, 28, 9, 0.5), (1, 28, 13, 0.7), (2, 24, 11, 0.6)])
+def test_mixed_k_layout_matches_vertical_layout_and_oracle(C, H, k, t, precision, monkeypatch):
+    """k > 8, k % 8 != 0: the trailing patch rows go through the rows8 plane as horizontal granules (query slices
+    resident in TMEM).  Must agree with the vertical-granule layout (CDS_ELS_MIXED=0) and with the float64 oracle."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
+    bank, labels = synthetic_bank(40, C, H, nlabels=3, seed=21)
+    beta = float(so.cosine_beta(t))
+    x = noisy_query(bank, beta, 2, seed=9)
+    res = {}
+    for mixed in ("1", "0"):
+        monkeypatch.setenv("CDS_ELS_MIXED", mixed)
+        mod = _make("ELS", (bank, labels), k, 16, None, precision=precision)
+        s = mod(torch.full((2,), t), x.cuda(), device=torch.device("cuda")).cpu().double().numpy()
+        res[mixed] = np.stack([_mu_from_score(s[b], x[b].double().numpy(), beta) for b in range(2)])
+    assert np.max(np.abs(res["1"] - res["0"])) < 2e-4
+    for b in range(2):
+        mu_o = _oracle_mu("ELS", x[b].numpy(), bank.numpy(), labels.numpy(), None, beta, k, 16)
+        assert np.max(np.abs(res["1"][b] - mu_o)) < MU_TOL
+
+
 def test_non8bit_bank_uses_residual_plane():
     """A bank that is not on the 8-bit grid needs the second bf16 plane to stay within tolerance."""
     from oracle import score_oracle as so
