@@ -273,6 +273,7 @@ extern "C" int cds_partials_simt(int kind, int query_pad, const float* x, int B,
 extern "C" int cds_pack_strip8(const float* images, int64_t N, int C, int H, int W, float scale, int plane,
                                void* out_f16, void* stream) {
   CDS_CHECK_ARG(N >= 1 && C >= 1 && H >= 1 && W >= 1, "cds_pack_strip8: empty bank");
+  CDS_CHECK_ARG(plane >= 0 && plane <= 2, "cds_pack_strip8: plane must be 0 (hi), 1 (residual) or 2 (rows8), got %d", plane);
   const long long total = (long long)N * C * H * W;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads > 148 * 32 ? 148 * 32 : (total + threads - 1) / threads);
