@@ -290,7 +290,7 @@ def run_ours(args, scales):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f16 operands (hi+lo query split where a/beta > 2.5), f32 accumulate/softmax" if args.precision != "f16" else "f16",
+            "dtype": "f16 operands (hi+lo query split where (a/beta)*k*sqrt(C) > 20), f32 accumulate/softmax" if args.precision != "f16" else "f16",
             "data": "synthetic",
             "config": {"workload": "els_cifar10_conditional", "bank": N_BANK, "image": [C, H, W], "scales": SCALES_NAME,
                        "evals_per_trajectory": len(scales) - 1, "batch": B, "precision": args.precision,

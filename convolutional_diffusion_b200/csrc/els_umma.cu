@@ -636,7 +636,7 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
     const char* f = getenv("CDS_DEBUG_FLAGS");
     p.flags = f ? atoi(f) : 0;
     const char* at = getenv("CDS_A_TMEM");     // A/B switch: 0 = every query slice from shared memory
-    if (at && atoi(at) == 0) p.g.n_tmem = 0;
+    if (at && atoi(at) == 0) p.g.n_tmem = p.g.n_h;   // the horizontal slices of the mixed layout exist only in TMEM
   }
   const int tiles = ((H + TI - 1) / TI) * ((W + TJ - 1) / TJ);
   dim3 grid(tiles, splits, B);

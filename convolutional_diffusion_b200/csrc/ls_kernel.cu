@@ -204,6 +204,7 @@ extern "C" int cds_ls_partials(const float* x, int B, int C, int H, int W, int k
   int ppt = (HW + 1023) / 1024;
   if (ppt == 3) ppt = 4;
   if (C == 3 && ppt < 2 && HW > 512) ppt = 2;          // keep the register footprint of tv[IB][PPT][C] in check
+  if (ppt == 2 && (HW + 1) / 2 > 512) ppt = 4;         // the two-pixel instantiation is bounded to 512 threads
   const int threads = ((HW + ppt - 1) / ppt + 31) / 32 * 32;
   LsParams p{B, C, H, W, k, splits, ppt, (long long)n_sel, x, beta, images, idx, logw, m, l, acc};
   const size_t smem = (size_t)images_per_round(C) * (H * (W + 2 * d) + (H + 2 * d) * W) * sizeof(float);

@@ -62,17 +62,20 @@ class ScoreEngine:
 
     def passes_for(self, k, beta_min):
         """Tensor-core passes over the query: 1 = fp16 query (11-bit significand), 2 = fp16 hi + lo residual
-        (22 bits, fp32-grade).  "auto" uses one pass while the logit gain a/beta that multiplies the dot-product
-        rounding error is <= 2.5.  Measured against the float64 oracle along the headline schedule
+        (22 bits, fp32-grade).  The query rounding error of one pass enters the logits as ~2^-12 (a/beta) sqrt(D),
+        D = k*k*C, so "auto" uses one pass while (a/beta) * sqrt(D) <= 20 (tightened to 20 * 30/sqrt(D) for D > 900).
+        Measured against the float64 oracle (tolerance 1e-3 on mu): along the headline schedule
         (tests/gpu_step_errors.py, 60-image bank, 4 seeds; profiles/r01g_step_errors.log) a single pass costs
-        2-4e-4 max-abs on mu for a/beta <= 2.4 (tolerance 1e-3), up to 7.8e-4 at a/beta = 3.2 and 1.5e-3 at 165,
-        so the low-noise steps keep the second pass (errors then ~1e-6)."""
+        <= 2.9e-4 inside that range, 2.0-4.1e-4 up to 30, 7.8e-4 at 38 (k=7, a/beta = 3.2) and 1.5e-3 at 850 (k=3,
+        a/beta = 165); on a 21-image bank with k=27 (tests/gpu_case_probe.py) 1.4e-3 at 27 and 2.0e-4 at 8.  Outside
+        the range the second pass brings the error to ~1e-5."""
         if self.precision == "f16":
             return 1
         if self.precision == "f16x2":
             return 2
         a_over_b = (max(1.0 - beta_min, 0.0) ** 0.5) / max(beta_min, 1e-6)
-        return 1 if a_over_b <= 2.5 else 2
+        root_d = k * self.bank.C ** 0.5
+        return 1 if a_over_b * root_d <= 20.0 * min(1.0, 30.0 / root_d) else 2
 
     def umma_supported(self, k, passes):
         b = self.bank

@@ -364,12 +364,12 @@ def test_random_geometries_against_oracle():
     counts, labels, ragged batches, max_samples) for all four module kinds against the float64 oracle."""
     from oracle import score_oracle as so
     from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
-    rng = np.random.default_rng(2024)
+    rng = np.random.default_rng(int(os.environ.get("CDS_FUZZ_SEED", "2024")))      # longer runs: CDS_FUZZ_TRIALS=400
     worst = 0.0
-    for trial in range(40):
+    for trial in range(int(os.environ.get("CDS_FUZZ_TRIALS", "40"))):
         kind = ["ELS", "bbELS", "LS", "IS"][trial % 4]
         C = int(rng.choice([1, 3]))
-        H = int(rng.integers(7, 25))
+        H = int(rng.integers(7, 25)) if trial % 5 else int(rng.integers(25, 41))
         kmax = H if kind == "ELS" else (H - 1 if kind == "bbELS" and trial % 8 else H + 4)
         k = int(rng.choice([v for v in range(3, max(4, kmax + 1), 2)]))
         N = int(rng.integers(3, 40))
@@ -377,6 +377,12 @@ def test_random_geometries_against_oracle():
         label = None if rng.random() < 0.5 else int(rng.integers(0, 3))
         ms = None if rng.random() < 0.7 else int(rng.integers(bs, N + bs))
         t = float(rng.uniform(0.03, 0.98))
+        # fp32 accumulation floor (reference and kernels alike): the dot products are O(k*k*C) in size and enter the
+        # logits times a/beta, so their fp32 resolution alone moves mu by ~1e-3 once (a/beta)*k*k*C reaches 1e5 (measured:
+        # 1.1e-3 at 1e5 with k=35, 1.7e-3 at 1.2e6 with k=31, both with the two-pass query).  The shipped schedules stay
+        # below 5e3 (large k only at high noise); fuzz up to 2e4.
+        while math.sqrt(1 - float(so.cosine_beta(t))) / float(so.cosine_beta(t)) * k * k * C > 2e4:
+            t = min(0.98, t + 0.05)
         bank, labels = synthetic_bank(N, C, H, nlabels=3, seed=100 + trial)
         if label is not None and not bool((labels == label).any()):
             label = int(labels[0])
