@@ -20,6 +20,7 @@ constexpr int MAXPPT = 4;  // pixels per thread (H*W <= 4096)
 
 struct LsParams {
   int B, C, H, W, k, splits, ppt;
+  int whole;   // window covers the whole image from every pixel (IS): one block-wide sum per image replaces the box filter
   long long n_sel;
   const float* x;
   const float* beta;
@@ -41,8 +42,10 @@ __global__ void __launch_bounds__(PPT == 2 ? 512 : 1024) ls_partials_kernel(LsPa
   const int split = blockIdx.x, b0 = blockIdx.y * SB;
   const int nb = min(SB, p.B - b0);
 
-  for (int e = tid; e < IB * H * Wp; e += nt) e_map[e] = 0.f;
-  for (int e = tid; e < IB * Hp * W; e += nt) r_map[e] = 0.f;
+  if (!p.whole) {
+    for (int e = tid; e < IB * H * Wp; e += nt) e_map[e] = 0.f;
+    for (int e = tid; e < IB * Hp * W; e += nt) r_map[e] = 0.f;
+  }
 
   int py[PPT], px[PPT];
   bool act[PPT];
@@ -86,6 +89,68 @@ __global__ void __launch_bounds__(PPT == 2 ? 512 : 1024) ls_partials_kernel(LsPa
       for (int j = 0; j < PPT; ++j)
 #pragma unroll
         for (int c = 0; c < C; ++c) tv[ib][j][c] = (on && act[j]) ? __ldg(img + c * HW + py[j] * W + px[j]) : 0.f;
+    }
+    // logits of one round for pixel j from its window sums -> online softmax (one max / one rescale per round)
+    auto update = [&](int s, int j, const float* box) {
+      float t[IB], tmax = -INFINITY;
+#pragma unroll
+      for (int ib = 0; ib < IB; ++ib) {
+        t[ib] = ib < ni ? fmaf(box[ib], sc_s[s], lw[ib]) : -INFINITY;
+        tmax = fmaxf(tmax, t[ib]);
+      }
+      Softmax2<C>& st = sm[s][j];
+      if (tmax > st.m) {
+        const float scl = exp2f(st.m - tmax);
+        st.l *= scl;
+#pragma unroll
+        for (int c = 0; c < C; ++c) st.acc[c] *= scl;
+        st.m = tmax;
+      }
+#pragma unroll
+      for (int ib = 0; ib < IB; ++ib) {
+        const float w = exp2f(t[ib] - st.m);
+        st.l += w;
+#pragma unroll
+        for (int c = 0; c < C; ++c) st.acc[c] = fmaf(w, tv[ib][j][c], st.acc[c]);
+      }
+    };
+    if (p.whole) {
+      // whole-image window (IS, idealscore.py:560-636): every pixel sees the same distance = block-wide sum
+      float* red = smem;                       // [IB][32] per-warp partial sums
+      const int warp = tid >> 5, lane = tid & 31, nw = (nt + 31) >> 5;
+#pragma unroll
+      for (int s = 0; s < SB; ++s) {
+        if (s >= nb) break;
+        float part[IB];
+#pragma unroll
+        for (int ib = 0; ib < IB; ++ib) {
+          part[ib] = 0.f;
+#pragma unroll
+          for (int j = 0; j < PPT; ++j)
+            if (act[j]) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const float df = fmaf(-a_s[s], tv[ib][j][c], xv[s][j][c]);
+                part[ib] = fmaf(df, df, part[ib]);
+              }
+            }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) part[ib] += __shfl_xor_sync(0xffffffffu, part[ib], off);
+          if (lane == 0) red[ib * 32 + warp] = part[ib];
+        }
+        __syncthreads();
+        float box[IB];
+#pragma unroll
+        for (int ib = 0; ib < IB; ++ib) {
+          box[ib] = 0.f;
+          for (int w = 0; w < nw; ++w) box[ib] += red[ib * 32 + w];      // same order in every thread
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (act[j]) update(s, j, box);
+        __syncthreads();
+      }
+      continue;
     }
 #pragma unroll
     for (int s = 0; s < SB; ++s) {
@@ -133,28 +198,7 @@ __global__ void __launch_bounds__(PPT == 2 ? 512 : 1024) ls_partials_kernel(LsPa
           for (int dy = 0; dy < k; ++dy)
 #pragma unroll
             for (int ib = 0; ib < IB; ++ib) box[ib] += col[(ib * Hp + dy) * W];
-          // one max / one rescale for the whole round instead of a branch per image
-          float t[IB], tmax = -INFINITY;
-#pragma unroll
-          for (int ib = 0; ib < IB; ++ib) {
-            t[ib] = ib < ni ? fmaf(box[ib], sc_s[s], lw[ib]) : -INFINITY;
-            tmax = fmaxf(tmax, t[ib]);
-          }
-          Softmax2<C>& st = sm[s][j];
-          if (tmax > st.m) {
-            const float scl = exp2f(st.m - tmax);
-            st.l *= scl;
-#pragma unroll
-            for (int c = 0; c < C; ++c) st.acc[c] *= scl;
-            st.m = tmax;
-          }
-#pragma unroll
-          for (int ib = 0; ib < IB; ++ib) {
-            const float w = exp2f(t[ib] - st.m);
-            st.l += w;
-#pragma unroll
-            for (int c = 0; c < C; ++c) st.acc[c] = fmaf(w, tv[ib][j][c], st.acc[c]);
-          }
+          update(s, j, box);
         }
       __syncthreads();
     }
@@ -206,8 +250,10 @@ extern "C" int cds_ls_partials(const float* x, int B, int C, int H, int W, int k
   if (C == 3 && ppt < 2 && HW > 512) ppt = 2;          // keep the register footprint of tv[IB][PPT][C] in check
   if (ppt == 2 && (HW + 1) / 2 > 512) ppt = 4;         // the two-pixel instantiation is bounded to 512 threads
   const int threads = ((HW + ppt - 1) / ppt + 31) / 32 * 32;
-  LsParams p{B, C, H, W, k, splits, ppt, (long long)n_sel, x, beta, images, idx, logw, m, l, acc};
-  const size_t smem = (size_t)images_per_round(C) * (H * (W + 2 * d) + (H + 2 * d) * W) * sizeof(float);
+  const int whole = d >= (H > W ? H : W) - 1 ? 1 : 0;
+  LsParams p{B, C, H, W, k, splits, ppt, whole, (long long)n_sel, x, beta, images, idx, logw, m, l, acc};
+  const size_t smem = whole ? (size_t)images_per_round(C) * 32 * sizeof(float)
+                            : (size_t)images_per_round(C) * (H * (W + 2 * d) + (H + 2 * d) * W) * sizeof(float);
   CDS_CHECK_ARG(smem <= 227 * 1024, "cds_ls_partials: kernel size %d too large for shared memory", k);
   dim3 grid(splits, (B + SB - 1) / SB);
   int rc = C == 1 ? launch_ls<1>(p, smem, grid, threads, (cudaStream_t)stream)

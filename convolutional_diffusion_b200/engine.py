@@ -130,6 +130,8 @@ class ScoreEngine:
         if self.lib.cds_ls_rows_supported(b.C, b.H, b.W, k):
             return True
         d = k // 2
+        if d >= max(b.H, b.W) - 1:                 # whole-image window (IS): block-wide sums, no box filter
+            return b.C in (1, 3) and b.H * b.W <= 4096
         smem = (8 if b.C == 1 else 4) * 4 * (b.H * (b.W + 2 * d) + (b.H + 2 * d) * b.W)   # images per round
         return b.C in (1, 3) and b.H * b.W <= 4096 and smem <= 227 * 1024
 
