@@ -97,6 +97,39 @@ def test_library_exports_every_declared_symbol():
     assert loaded.cds_els_umma_smem_bytes(3, 32, 32, 4, 1, 1) == 0       # even kernel sizes are rejected
 
 
+def test_umma_geometry_choices():
+    """Host-side tiling decisions of the tensor-core kernel (printed with CDS_DEBUG_GEOM; the launch itself fails
+    without a GPU): CIFAR shape, one query pass.  The mixed K layout must keep the band height of the vertical layout
+    and is taken for k = 9, 11, 13, 17 (17/28, 26/34, 35/40, 57/77 UMMAs per tile) but not for k = 15 (44/46)."""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from convolutional_diffusion_b200 import _lib\n"
+        "lib = _lib.load()\n"
+        "one = ctypes.c_void_p(16)\n"
+        "for k in (5, 9, 11, 13, 15, 17):\n"
+        "    lib.cds_els_partials_umma(1, None, 4, 3, 32, 32, k, None, None, None, one, 255.0, None, None, None, 100, 9, 1,\n"
+        "                              None, None, None, None, None)\n" % ROOT)
+    env = dict(os.environ, CDS_DEBUG_GEOM="1", CUDA_VISIBLE_DEVICES="")      # never launch: the pointers are dummies
+    env.pop("CDS_ELS_MIXED", None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    geo = {}
+    for line in r.stderr.splitlines():
+        m = re.search(r"els_umma k=(\d+) .* mixed=(\d) G=(\d+) chunks=(\d+) nvb=(\d+) n_mma=(\d+) n_tmem=(\d+) stages=(\d+) smem=(\d+)", line)
+        if m:
+            v = [int(g) for g in m.groups()]
+            geo[v[0]] = dict(mixed=v[1], G=v[2], chunks=v[3], nvb=v[4], n_mma=v[5], n_tmem=v[6], stages=v[7], smem=v[8])
+    assert set(geo) == {5, 9, 11, 13, 15, 17}, (r.stderr[-500:], r.stdout[-200:])
+    assert [geo[k]["mixed"] for k in (5, 9, 11, 13, 15, 17)] == [0, 1, 1, 1, 0, 1]
+    assert [geo[k]["n_mma"] for k in (5, 9, 11, 13, 15, 17)] == [8, 17, 26, 35, 46, 57]
+    assert [geo[k]["G"] for k in (5, 9, 11, 13, 15, 17)] == [28, 24, 22, 20, 18, 16]       # one band = all patch rows
+    for k, g in geo.items():
+        assert g["stages"] == 2 and g["chunks"] == 1 and g["smem"] <= 227 * 1024, (k, g)
+        assert 16 * g["G"] + 8 * g["n_tmem"] <= 512, (k, g)                              # TMEM columns
+
+
 def test_no_cpu_fallback():
     """Without CUDA the product path must fail loudly, not fall back."""
     if torch.cuda.is_available():
