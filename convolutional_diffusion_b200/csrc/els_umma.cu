@@ -22,9 +22,15 @@
 //   * One UMMA covers N = 8 * (#patch rows) <= 256 candidates x 128 queries x K = 16; accumulators ping-pong
 //     between two TMEM buffers.  Warp roles: producer (bulk copies), MMA issuer (one thread), two builder warps
 //     (centre-pixel tables per image) and four epilogue warpgroups, decoupled through mbarriers.
-//   * Epilogue = flash softmax in two passes per 16-column chunk: (1) tcgen05.ld + 3-input max; a chunk whose
-//     best logit is 2^-40 below the running max for all 32 queries of the warp is skipped; (2) packed f32x2
-//     fma -> ex2 -> weighted sums.
+//   * Mixed K layout (k > 8, k % 8 != 0, single-plane bank): the trailing k % 8 patch rows are contracted as horizontal
+//     8-pixel granules from the "rows8" plane instead of one more mostly-empty vertical block (k=9: 17 UMMAs per tile
+//     instead of 28).  Their query slices cannot alias, so they live only in TMEM (built once in the staging area).
+//   * Query K slices stay resident in the TMEM columns the two accumulator buffers leave free: those UMMAs read A from
+//     TMEM and only B from shared memory (the data pipe they share with the epilogue's loads was 95 % busy).
+//   * Epilogue = flash softmax in two passes per 16-column chunk on the 16x256b TMEM fragment (four query rows x four
+//     columns per thread, so one 16-byte centre-pixel load per channel serves 16 pairs): (1) tcgen05.ld + 3-input max;
+//     a chunk whose best logit is 2^-40 below the running max for every row of the warp is skipped; (2) packed f32x2
+//     fma -> ex2 -> weighted sums.  Floor = 8 cycles per candidate column twice over (TMEM read bandwidth, MUFU).
 #include <type_traits>
 #include "umma_common.cuh"
 

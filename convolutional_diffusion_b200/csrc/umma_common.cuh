@@ -72,8 +72,8 @@ struct UmmaParams {
   const int32_t* idx;
   const float* logw;
   float *m, *l, *acc, *dbg;
-  int flags;               // profiling switches (CDS_DEBUG_FLAGS): 1 = skip pass 2, 2 = skip the whole epilogue math (a third switch that dropped the centre-pixel table
-                           // loads sat in the innermost loop and cost 30 % by itself; removed)
+  int flags;               // profiling switches, honoured only when built with -DCDS_PROFILE_SWITCHES (CDS_DEBUG_FLAGS):
+                           // 1 = pass 1 only, 2 = UMMAs only (no epilogue math), 8 = epilogue only (no UMMAs issued)
   uint2 table[MAX_MMAS];   // lo words of the (A,B) descriptors relative to the A base / the tile origin in a stage
 };
 
