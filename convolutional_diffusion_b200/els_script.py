@@ -78,6 +78,8 @@ def main(argv=None):
     ap.add_argument("--numiters", type=int, default=100)
     ap.add_argument("--nsteps", type=int, default=20)
     ap.add_argument("--nlabels", type=int, default=10)
+    ap.add_argument("--samplebatch", type=int, default=1,
+                    help="samples generated per machine call (extension; labels are drawn per sample)")
     ap.add_argument("--force_overwrite", action="store_true", default=False)
     ap.add_argument("--max_samples", type=int, default=100000)
     ap.add_argument("--shuffle", action="store_true", default=False)
@@ -127,14 +129,18 @@ def main(argv=None):
         start = 0
     for pth in (seedpath, spath) + ((lpath,) if args.conditional else ()):
         os.makedirs(pth, exist_ok=True)
-    for i in range(start, args.numiters):
-        seed = torch.randn(1, channels, image_size, image_size, device=device)
-        label = torch.randint(0, args.nlabels, (1,)) if args.conditional else None
-        out = machine(seed.clone(), label=label, device=device)
-        torch.save(seed.cpu(), os.path.join(seedpath, f"{i:04d}.pt"))
-        torch.save(out.cpu(), os.path.join(spath, f"{i:04d}.pt"))
-        if args.conditional:
-            torch.save(label, os.path.join(lpath, f"{i:04d}.pt"))
+    i = start
+    while i < args.numiters:
+        nb = max(1, min(args.samplebatch, args.numiters - i))     # samples per machine call (the reference: 1)
+        seeds = torch.randn(nb, channels, image_size, image_size, device=device)
+        labels = torch.randint(0, args.nlabels, (nb,)) if args.conditional else None
+        outs = machine(seeds.clone(), label=labels, device=device)
+        for j in range(nb):                                       # same per-sample files as the reference writes
+            torch.save(seeds[j:j + 1].cpu(), os.path.join(seedpath, f"{i + j:04d}.pt"))
+            torch.save(outs[j:j + 1].cpu(), os.path.join(spath, f"{i + j:04d}.pt"))
+            if args.conditional:
+                torch.save(labels[j:j + 1].clone(), os.path.join(lpath, f"{i + j:04d}.pt"))
+        i += nb
     return args.numiters
 
 

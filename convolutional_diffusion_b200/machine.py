@@ -15,7 +15,7 @@ import math
 import torch
 from torch import nn
 
-from .modules import _ScoreModuleBase, _as_label, cosine_noise_schedule
+from .modules import _ScoreModuleBase, _as_label, _label_groups, cosine_noise_schedule
 
 
 def ddim_coefficients(nsteps, schedule=cosine_noise_schedule):
@@ -53,6 +53,15 @@ class ScheduledScoreMachine(nn.Module):
             nsteps = self.default_time_steps if self.scales is None else len(self.scales)
         native = isinstance(self.backbone, _ScoreModuleBase) and self.score_backbone \
             and self.backbone.schedule is self.noise_schedule
+        groups = _label_groups(label, x.shape[0]) if native else None
+        if groups is not None:                   # per-sample labels: one trajectory per distinct label
+            out = None
+            for lab_g, rows in groups.items():
+                res = self._forward_native(x[rows], nsteps, lab_g, torch.device(device))
+                if out is None:
+                    out = torch.empty((x.shape[0],) + tuple(res.shape[1:]), dtype=res.dtype, device=res.device)
+                out[torch.as_tensor(rows, device=res.device)] = res
+            return out
         if native:
             return self._forward_native(x, nsteps, _as_label(label), torch.device(device))
         return self._forward_generic(x, nsteps, label, device)

@@ -45,6 +45,22 @@ def _as_label(label):
     return int(label)
 
 
+def _label_groups(label, B):
+    """Per-sample labels (an extension; the reference is b = 1 with one label per call): a label tensor
+    / sequence with B > 1 entries that are not all equal -> {label: [sample indices]}; otherwise None."""
+    if label is None or B <= 1:
+        return None
+    flat = label.reshape(-1).tolist() if torch.is_tensor(label) else (list(label) if hasattr(label, "__len__") else None)
+    if flat is None or len(flat) == 1:
+        return None
+    if len(flat) != B:
+        raise ValueError(f"label has {len(flat)} entries for a batch of {B} samples (expected 1 or {B})")
+    groups = {}
+    for i, v in enumerate(flat):
+        groups.setdefault(int(v), []).append(i)
+    return groups if len(groups) > 1 else None
+
+
 class _ScoreModuleBase(nn.Module):
     kind = None
     query_pad = None
@@ -114,6 +130,13 @@ class _ScoreModuleBase(nn.Module):
         tt = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
         if tt.numel() == 1 and xd.shape[0] > 1:
             tt = tt.expand(xd.shape[0])
+        groups = _label_groups(label, xd.shape[0])
+        if groups is not None:                   # one evaluation per distinct label, results scattered back
+            out = torch.empty_like(xd)
+            for lab_g, rows in groups.items():
+                sel_rows = torch.as_tensor(rows, device=xd.device)
+                out[sel_rows] = self.forward(tt[rows], xd[sel_rows], label=lab_g, device=device, k=k)
+            return out
         beta_cpu = self.schedule(tt.cpu().float())
         beta = beta_cpu.to(eng.device, torch.float32).contiguous()
         lab = _as_label(label)

@@ -285,6 +285,29 @@ def test_cifar_schedule_every_step(precision):
     print(f"precision={precision}: worst per-step mu error {worst:.2e}, final PSNR {psnr:.1f} dB")
 
 
+def test_per_sample_labels_equal_separate_calls():
+    """Extension of the b = 1 reference call: a batch with one label per sample == the samples evaluated one by one,
+    for a single score evaluation and for a whole trajectory."""
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    cd = _mods()
+    bank, labels = synthetic_bank(40, 3, 16, nlabels=3, seed=4)
+    mod = _make("ELS", (bank, labels), 5, 16, None)
+    x = torch.randn(4, 3, 16, 16, generator=torch.Generator().manual_seed(8)).cuda()
+    lab = torch.tensor([2, 0, 2, 1])
+    t = torch.tensor([0.3, 0.5, 0.7, 0.4])
+    s = mod(t, x, label=lab, device=torch.device("cuda"))
+    for b in range(4):
+        sb = mod(t[b:b + 1], x[b:b + 1], label=lab[b:b + 1], device=torch.device("cuda"))
+        assert torch.allclose(s[b], sb[0], atol=1e-5, rtol=1e-5), b
+    machine = cd.ScheduledScoreMachine(mod, in_channels=3, imsize=16, scales=[3, 3, 5, 5, 7])
+    out = machine(x, label=lab, device=torch.device("cuda"))
+    for b in range(4):
+        ob = machine(x[b:b + 1], label=lab[b:b + 1], device=torch.device("cuda"))
+        assert torch.allclose(out[b], ob[0], atol=1e-5, rtol=1e-5), b
+    with pytest.raises(ValueError):
+        mod(t, x, label=torch.tensor([0, 1, 2]), device=torch.device("cuda"))
+
+
 def test_els_script_layout_and_resume(tmp_path):
     """Drop-in driver: per-sample files results/<exp>/{seeds,els_outputs,labels}/NNNN.pt, resume, --fill."""
     from convolutional_diffusion_b200 import els_script
@@ -302,6 +325,13 @@ def test_els_script_layout_and_resume(tmp_path):
     assert len(os.listdir(d / "seeds")) == 3
     els_script.main(common + ["--fill", "--idealname", "ideal", "--scoremoduletype", "IS"])   # same seeds, IS outputs
     assert sorted(os.listdir(d / "ideal")) == ["0000.pt", "0001.pt", "0002.pt"]
+    # batched generation (extension): several samples per machine call, labels per sample, same per-sample files
+    els_script.main(common[:-1] + ["tb", "--numiters", "7", "--samplebatch", "3"])
+    db = tmp_path / "tb"
+    for sub in ("seeds", "els_outputs", "labels"):
+        assert sorted(os.listdir(db / sub)) == [f"{i:04d}.pt" for i in range(7)]
+    assert torch.load(db / "els_outputs" / "0006.pt").shape == (1, 3, 32, 32)
+    assert torch.load(db / "labels" / "0005.pt").shape == (1,)
 
 
 def test_calibration_recovers_the_kernel_size_of_an_analytic_model():
