@@ -130,6 +130,19 @@ def test_umma_geometry_choices():
         assert 16 * g["G"] + 8 * g["n_tmem"] <= 512, (k, g)                              # TMEM columns
 
 
+def test_label_groups():
+    """Per-sample labels: grouping helper behind modules.forward / ScheduledScoreMachine.forward."""
+    from convolutional_diffusion_b200.modules import _label_groups
+    assert _label_groups(None, 4) is None
+    assert _label_groups(torch.tensor([3]), 4) is None                  # one label for the whole call (the reference)
+    assert _label_groups(torch.tensor([3, 3, 3]), 3) is None            # all equal: a single evaluation
+    assert _label_groups(torch.tensor([2, 0, 2, 1]), 4) == {2: [0, 2], 0: [1], 1: [3]}
+    assert _label_groups([1, 0], 2) == {1: [0], 0: [1]}
+    assert _label_groups(5, 4) is None
+    with pytest.raises(ValueError):
+        _label_groups(torch.tensor([0, 1, 2]), 4)
+
+
 def test_no_cpu_fallback():
     """Without CUDA the product path must fail loudly, not fall back."""
     if torch.cuda.is_available():
