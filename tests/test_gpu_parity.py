@@ -308,6 +308,16 @@ def test_per_sample_labels_equal_separate_calls():
         mod(t, x, label=torch.tensor([0, 1, 2]), device=torch.device("cuda"))
 
 
+def test_raw_c_abi_binding_of_integration_md():
+    """The ctypes-only binding printed in INTEGRATION.md section B (no package code on the call path)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gpu_integration_snippet",
+                                                  os.path.join(os.path.dirname(__file__), "gpu_integration_snippet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
+
+
 def test_els_script_layout_and_resume(tmp_path):
     """Drop-in driver: per-sample files results/<exp>/{seeds,els_outputs,labels}/NNNN.pt, resume, --fill."""
     from convolutional_diffusion_b200 import els_script
