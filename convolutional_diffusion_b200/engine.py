@@ -125,6 +125,12 @@ class ScoreEngine:
         self.launches += 1
         return P
 
+    def simt_supported(self, k):
+        """The generic kernel keeps the padded query and one padded bank image in shared memory."""
+        b = self.bank
+        d = k // 2
+        return 2 * b.C * (b.H + 2 * d) * (b.W + 2 * d) * 4 <= 227 * 1024
+
     def ls_supported(self, k):
         b = self.bank
         if self.lib.cds_ls_rows_supported(b.C, b.H, b.W, k):
@@ -236,7 +242,9 @@ class ScoreEngine:
         if kind == "IS":                          # whole-image window: the LS kernel with k = 2*max(H,W)-1
             kind, k = "LS", 2 * max(b.H, b.W) - 1
         if kind == "LS":
-            if self.use_tensor_cores and self.ls_supported(k):
+            # use_tensor_cores=False asks for the generic exact-fp32 kernel; the streaming LS kernels are fp32 SIMT as
+            # well and take over where the generic one cannot hold the padded planes (IS on images above 32 pixels)
+            if self.ls_supported(k) and (self.use_tensor_cores or not self.simt_supported(k)):
                 P = self.ls_partials(x, beta, k, sel)
             else:
                 P = self.simt_partials("LS", "zeros", x, beta, k, sel)

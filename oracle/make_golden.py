@@ -44,6 +44,25 @@ def _module(ref, kind, ds, k, bs, max_samples):
     raise ValueError(kind)
 
 
+def _one_module_case(ref, kind, c, h, n, k, t, label, bs, ms, seed):
+    bank, labels = synthetic_bank(n, c, h, nlabels=4, seed=seed)
+    g = torch.Generator().manual_seed(100 + seed)
+    j = int(torch.randint(0, n, (1,), generator=g))
+    tt = torch.tensor([t])
+    beta = float(ref.cosine_noise_schedule(tt))
+    x = (1 - beta) ** 0.5 * bank[j:j + 1] + beta ** 0.5 * torch.randn(1, c, h, h, generator=g)
+    ds = ref_loader.TensorBank(bank, labels)
+    torch.manual_seed(0)
+    mod = _module(ref, kind, ds, k, bs, ms)
+    lab = None if label is None else torch.tensor([label])
+    with torch.no_grad():
+        s = mod(tt, x.clone(), label=lab, device=torch.device("cpu"))
+    print(f"module {kind:5s} C={c} H={h} N={n} k={k} t={t} label={label}: |score|max={s.abs().max():.3f}")
+    return dict(kind=kind, bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(), t=np.float64(t),
+                k=np.int64(k), label=np.int64(-1 if label is None else label),
+                batch_size=np.int64(bs), max_samples=np.int64(-1 if ms is None else ms), score=s.numpy())
+
+
 def module_cases(ref):
     cases = []
     # (kind, C, H, N, k, t, label, batch_size, max_samples, bank_seed)
@@ -70,23 +89,7 @@ def module_cases(ref):
         ("IS", 3, 32, 24, 3, 0.85, None, 24, None, 5),
     ]
     for kind, c, h, n, k, t, label, bs, ms, seed in spec:
-        bank, labels = synthetic_bank(n, c, h, nlabels=4, seed=seed)
-        g = torch.Generator().manual_seed(100 + seed)
-        j = int(torch.randint(0, n, (1,), generator=g))
-        tt = torch.tensor([t])
-        beta = float(ref.cosine_noise_schedule(tt))
-        x = (1 - beta) ** 0.5 * bank[j:j + 1] + beta ** 0.5 * torch.randn(1, c, h, h, generator=g)
-        ds = ref_loader.TensorBank(bank, labels)
-        torch.manual_seed(0)
-        mod = _module(ref, kind, ds, k, bs, ms)
-        lab = None if label is None else torch.tensor([label])
-        with torch.no_grad():
-            s = mod(tt, x.clone(), label=lab, device=torch.device("cpu"))
-        cases.append(dict(kind=kind, bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(), t=np.float64(t),
-                          k=np.int64(k), label=np.int64(-1 if label is None else label),
-                          batch_size=np.int64(bs), max_samples=np.int64(-1 if ms is None else ms),
-                          score=s.numpy()))
-        print(f"module {kind:5s} C={c} H={h} N={n} k={k} t={t} label={label}: |score|max={s.abs().max():.3f}")
+        cases.append(_one_module_case(ref, kind, c, h, n, k, t, label, bs, ms, seed))
     # bbELS with k >= H delegates to its internal LS (idealscore.py:163-164); single batch so the
     # hard-coded shuffle=True cannot change the result
     bank, labels = synthetic_bank(16, 3, 8, nlabels=4, seed=7)
@@ -99,6 +102,17 @@ def module_cases(ref):
     cases.append(dict(kind="bbELS", bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(), t=np.float64(0.6),
                       k=np.int64(9), label=np.int64(-1), batch_size=np.int64(16), max_samples=np.int64(-1),
                       score=s.numpy()))
+    # added later (appended so that the earlier files keep their numbers): kernel sizes whose trailing rows go through
+    # the mixed K layout of the tensor-core kernel, and IS on an image larger than 32 pixels
+    more = [
+        ("ELS", 3, 32, 24, 9, 0.60, None, 16, None, 8),
+        ("ELS", 3, 32, 16, 13, 0.75, 2, 8, None, 9),
+        ("ELS", 1, 28, 24, 11, 0.65, None, 24, None, 10),
+        ("ELS", 3, 32, 12, 17, 0.90, None, 12, None, 11),
+        ("IS", 3, 40, 12, 3, 0.50, None, 12, None, 12),
+    ]
+    for kind, c, h, n, k, t, label, bs, ms, seed in more:
+        cases.append(_one_module_case(ref, kind, c, h, n, k, t, label, bs, ms, seed))
     return cases
 
 
@@ -149,12 +163,20 @@ def main():
     ref = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    force = "--force" in sys.argv          # default: keep the committed fixtures, write only the ones that are missing
+
+    def save(name, arrays):
+        path = os.path.join(OUT, name)
+        if force or not os.path.exists(path):
+            np.savez_compressed(path, **arrays)
+            print("wrote", name)
+
     for i, c in enumerate(module_cases(ref)):
-        np.savez_compressed(os.path.join(OUT, f"module_{i:02d}_{c['kind']}.npz"), **c)
+        save(f"module_{i:02d}_{c['kind']}.npz", c)
     for i, c in enumerate(machine_cases(ref)):
-        np.savez_compressed(os.path.join(OUT, f"machine_{i:02d}_{c['kind']}.npz"), **c)
-    np.savez_compressed(os.path.join(OUT, "schedule.npz"), **schedule_cases(ref))
-    np.savez_compressed(os.path.join(OUT, "scales.npz"), **scales_files())
+        save(f"machine_{i:02d}_{c['kind']}.npz", c)
+    save("schedule.npz", schedule_cases(ref))
+    save("scales.npz", scales_files())
 
 
 if __name__ == "__main__":
