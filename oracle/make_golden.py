@@ -124,6 +124,10 @@ def machine_cases(ref):
         ("bbELS", 3, 12, 32, [3, 3, 3, 5, 5, 7], None, 16, 10),
         ("bbELS", 1, 12, 36, [3, 3, 5, 5, 7, 7, 9, 13], 2, 12, 11),   # last k >= H -> LS fallback, 1 batch/class
         ("LS", 3, 12, 32, [3, 3, 3, 5, 5, 7], None, 32, 10),
+        # added later (appended): the headline geometry with the kernel sizes of the shipped CIFAR schedule, and a
+        # MNIST-shape run with a non-monotone schedule like scales_MNIST_ResNet_circular
+        ("ELS", 3, 32, 20, [3, 3, 5, 7, 9, 11, 13, 15, 17, 17], 1, 8, 12),
+        ("ELS", 1, 28, 24, [3, 3, 5, 7, 11, 11, 9, 7, 3], None, 10, 13),
     ]
     for kind, c, h, n, scales, label, bs, seed in spec:
         bank, labels = synthetic_bank(n, c, h, nlabels=3, seed=seed)
