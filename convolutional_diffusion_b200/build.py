@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcdscore.so")
 SOURCES = ["api.cu", "simt_kernels.cu", "ls_kernel.cu", "ls_rows_kernel.cu", "bbels_edge.cu", "els_umma.cu", "els_umma_pv.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-shared"]
+         "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]      # --threads 0: compile the sources in parallel
 
 
 def _stale():
