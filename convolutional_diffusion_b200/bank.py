@@ -56,6 +56,8 @@ class PatchBank:
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError(f"PatchBank device must be CUDA, got {self.device}")
+        if self.device.index is None:                            # always a concrete ordinal: tensors report cuda:N
+            self.device = torch.device("cuda", torch.cuda.current_device())
         assert images.dim() == 4, "bank images must be [N,C,H,W]"
         self.images = images.to(self.device, torch.float32).contiguous()
         self.labels = np.asarray(torch.as_tensor(labels).cpu()).astype(np.int64).reshape(-1)

@@ -24,19 +24,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
-        return OUT
+def build(force=False, verbose=False, profile=False):
+    """profile=True builds libcdscore_prof.so with -DCDS_PROFILE_SWITCHES (A/B switches and skip counters of the
+    tcgen05 kernel; selected at run time with CDS_LIB_PATH) -- never the product library."""
+    out = OUT.replace(".so", "_prof.so") if profile else OUT
+    if not force and not profile and not _stale():
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + srcs
+    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCDS_PROFILE_SWITCHES"] if profile else []) \
+        + ["-o", out] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))

@@ -38,6 +38,12 @@ using namespace umma;
 
 namespace {
 
+#ifdef CDS_PROFILE_SWITCHES
+// profile builds only: [0] warp-chunks seen, [1] warp-chunks skipped (all weights < 2^-40 of the running max),
+// [2] warp-chunks that raised a running max, [3] (warp, tile) units seen, [4] (warp, tile) units with every chunk skipped
+__device__ unsigned long long g_els_counters[8];
+#endif
+
 // ------------------------------------------------------------------ the kernel
 template <int C>
 __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_constant__ UmmaParams p) {
@@ -332,6 +338,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 #ifdef CDS_PROFILE_SWITCHES
     const bool prof_pass1_only = (p.flags & 1) != 0, prof_mma_only = (p.flags & 2) != 0;   // CDS_DEBUG_FLAGS
 #endif
+#ifdef CDS_PROFILE_SWITCHES
+    unsigned cnt_chunks = 0, cnt_skipped = 0, cnt_rescale = 0, cnt_tiles = 0, cnt_tiles_skipped = 0;
+#endif
     uint32_t T = 0;
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
@@ -409,6 +418,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             // every weight of this chunk is < 2^-40 of the running max for all rows of the warp: adding them
             // cannot change an fp32 sum (<= 4.5e6 candidates * 2^-40 = 4e-6 relative in the worst case)
             const float lead = fmaxf(max3(cm[0] - m4[0], cm[1] - m4[1], cm[2] - m4[2]), cm[3] - m4[3]);
+#ifdef CDS_PROFILE_SWITCHES
+            ++cnt_chunks;
+            if (__all_sync(0xffffffffu, lead < -SKIP_LOG2)) { ++cnt_skipped; return; }
+            if (__any_sync(0xffffffffu, lead > 0.f)) ++cnt_rescale;
+#endif
             if (__all_sync(0xffffffffu, lead < -SKIP_LOG2)) return;
 #ifdef CDS_PROFILE_SWITCHES
             if (prof_pass1_only) {     // profiling: pass 1 only
@@ -471,8 +485,15 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               chunk(ra, c0, pv, slow);
             }
           };
+#ifdef CDS_PROFILE_SWITCHES
+          const unsigned c_before = cnt_chunks, s_before = cnt_skipped;
+#endif
           if (edge || dump) sweep(std::true_type{});
           else sweep(std::false_type{});
+#ifdef CDS_PROFILE_SWITCHES
+          ++cnt_tiles;
+          if (cnt_chunks - c_before == cnt_skipped - s_before) ++cnt_tiles_skipped;
+#endif
           tc_fence_before();
           __syncwarp();
           if (elect_one()) mbar_arrive(bar_t + 16 + 8 * buf);
@@ -481,6 +502,15 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         if (elect_one()) mbar_arrive(bar_empty + 8 * s);
       }
     }
+#ifdef CDS_PROFILE_SWITCHES
+    if (lane == 0) {
+      atomicAdd(&g_els_counters[0], (unsigned long long)cnt_chunks);
+      atomicAdd(&g_els_counters[1], (unsigned long long)cnt_skipped);
+      atomicAdd(&g_els_counters[2], (unsigned long long)cnt_rescale);
+      atomicAdd(&g_els_counters[3], (unsigned long long)cnt_tiles);
+      atomicAdd(&g_els_counters[4], (unsigned long long)cnt_tiles_skipped);
+    }
+#endif
     // the four threads t4 = 0..3 of a row group hold the same four rows over disjoint columns: merge them with shuffles,
     // after which thread (tr, t4) owns row tr + 8*t4 of its warp's 32
     float m = -INFINITY, l = 0.f, acc[C];
@@ -580,6 +610,17 @@ __global__ void norm_plane_kernel(const float* __restrict__ images, long long N,
 }
 
 }  // namespace
+
+#ifdef CDS_PROFILE_SWITCHES
+// profile builds only (not part of include/cdscore.h): copies the counters to the host (synchronises) and clears them
+extern "C" int cds_debug_els_counters(unsigned long long* out_host8) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out_host8, g_els_counters, sizeof(g_els_counters));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_els_counters, z, sizeof(z));
+  return e == cudaSuccess ? CDS_OK : CDS_ERR_CUDA;
+}
+#endif
 
 extern "C" int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes) {
   UmmaGeom g;

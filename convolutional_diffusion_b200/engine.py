@@ -233,14 +233,22 @@ class ScoreEngine:
         b = self.bank
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         assert tuple(x.shape[1:]) == (b.C, b.H, b.W), f"x {tuple(x.shape)} does not match bank {(b.C, b.H, b.W)}"
-        if k % 2 == 0 or k < 1:
+        if x.device != self.device:
+            raise RuntimeError(f"x lives on {x.device} but the bank of this engine on {self.device}")
+        # the raw launches below go to the CURRENT device's stream: make the engine's device current for their duration
+        with torch.cuda.device(self.device):
+            return self._evaluate(kind, x, beta, k, sel, query_pad, mu, score, beta_min, sel_ls)
+
+    def _evaluate(self, kind, x, beta, k, sel, query_pad, mu, score, beta_min, sel_ls):
+        b = self.bank
+        if kind == "IS":                          # whole-image window: the LS kernel with k = 2*max(H,W)-1; the
+            kind, k = "LS", 2 * max(b.H, b.W) - 1  # reference IS ignores k altogether (idealscore.py:583, **kwargs)
+        if k is None or k % 2 == 0 or k < 1:
             raise ValueError(f"kernel size must be odd and positive, got {k}")
         if beta_min is None:
             beta_min = float(beta.min())         # host sync; the machine passes beta_min explicitly
         if kind == "bbELS" and k >= b.H:          # idealscore.py:163-164: delegate to the internal LS module
             kind, sel = "LS", (sel_ls if sel_ls is not None else sel)
-        if kind == "IS":                          # whole-image window: the LS kernel with k = 2*max(H,W)-1
-            kind, k = "LS", 2 * max(b.H, b.W) - 1
         if kind == "LS":
             # use_tensor_cores=False asks for the generic exact-fp32 kernel; the streaming LS kernels are fp32 SIMT as
             # well and take over where the generic one cannot hold the padded planes (IS on images above 32 pixels)

@@ -41,9 +41,12 @@ class ScheduledScoreMachine(nn.Module):
         self.in_channels = in_channels
         self.imsize = imsize
         self.score_backbone = score_backbone
-        self.scales = scales
+        # plain ints: calibrate()['median'] and torch.load results arrive as tensors, whose 0-d elements hash by identity
+        # (a graph-cache miss on every call) -- normalise once
+        self.scales = None if scales is None else [int(s) for s in (scales.tolist() if torch.is_tensor(scales) else scales)]
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
+        self.max_cached_graphs = 32          # (nsteps, B, label, scales) keys; oldest evicted beyond this
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x, nsteps=None, label=None, device=None, visualize=False):
@@ -105,9 +108,21 @@ class ScheduledScoreMachine(nn.Module):
                               cmu=torch.full((B,), cmu, dtype=torch.float32, device=device)))
         return steps
 
-    def _run_steps(self, eng, steps, x, mu, sel, sel_ls, record=None):
+    def _run_steps(self, eng, steps, x, mu, sel, sel_ls, record=None, label=None, reselect=False):
+        """reselect: the visiting order is shuffled (LS, shuffle=True, or the bbELS -> LS delegation with
+        batch_size < N).  The reference opens a fresh DataLoader iterator per score evaluation (idealscore.py:184,430,521),
+        i.e. a new permutation -- and two global RNG draws -- at every step, so the selection is redrawn per step
+        (eager path only; a captured graph would freeze one permutation)."""
         mod = self.backbone
         for st in steps:
+            if reselect:
+                if mod.kind == "bbELS":
+                    if st["k"] >= eng.bank.H:
+                        sel_ls = mod.selection(label, kind="LS")
+                    elif mod.shuffle:
+                        sel = mod.selection(label)
+                else:
+                    sel = mod.selection(label)
             eng.evaluate(mod.kind, x, st["beta_dev"], st["k"], sel, query_pad=mod.query_pad, mu=mu, score=None,
                          beta_min=st["beta"], sel_ls=sel_ls)
             if record is not None:
@@ -118,18 +133,25 @@ class ScheduledScoreMachine(nn.Module):
         mod = self.backbone
         eng = mod.engine(device)
         B = x.shape[0]
-        sel = mod.selection(label)
         needs_ls = mod.kind == "bbELS" and any(
             (mod.kernel_size if self.scales is None else int(s)) >= eng.bank.H
             for s in (self.scales[1:nsteps] if self.scales is not None else [mod.kernel_size]))
-        sel_ls = mod.selection(label, kind="LS") if needs_ls else None
         shuffled = mod.shuffle or (mod.kind == "LS" and mod._ls_shuffles()) or needs_ls and mod._ls_shuffles()
+        if shuffled:
+            # drawn per step inside _run_steps (one permutation = two global RNG draws per evaluation, as in the
+            # reference); only the deterministic part is resolved here
+            sel = mod.selection(label) if (mod.kind == "bbELS" and not mod.shuffle) else None
+            sel_ls = None
+        else:
+            sel = mod.selection(label)
+            sel_ls = mod.selection(label, kind="LS") if needs_ls else None
         key = (nsteps, B, label, tuple(self.scales) if self.scales is not None else None)
         with torch.cuda.device(eng.device):
             if record is not None or not self.use_cuda_graph or shuffled:
                 xw = x.to(eng.device, torch.float32).clone().contiguous()
                 mu = torch.empty_like(xw)
-                self._run_steps(eng, self._plan(nsteps, B, eng.device), xw, mu, sel, sel_ls, record)
+                self._run_steps(eng, self._plan(nsteps, B, eng.device), xw, mu, sel, sel_ls, record, label=label,
+                                reselect=bool(shuffled))
                 return xw
             if key not in self._graphs:
                 steps = self._plan(nsteps, B, eng.device)
@@ -145,6 +167,8 @@ class ScheduledScoreMachine(nn.Module):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     self._run_steps(eng, steps, xs, mu, sel, sel_ls)
+                while len(self._graphs) >= self.max_cached_graphs:
+                    self._graphs.pop(next(iter(self._graphs)))
                 self._graphs[key] = (graph, xs, mu, steps, sel, sel_ls)
             graph, xs, mu, *_ = self._graphs[key]
             xs.copy_(x.to(eng.device, torch.float32))

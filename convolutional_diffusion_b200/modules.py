@@ -83,6 +83,11 @@ class _ScoreModuleBase(nn.Module):
 
     # -- lazily built device state ----------------------------------------------------------------
     def engine(self, device=None) -> ScoreEngine:
+        if self._engine is not None and device is not None:
+            want = torch.device(device)
+            if want.type == "cuda" and want.index is not None and want != self._engine.device:
+                raise RuntimeError(f"this score module's bank lives on {self._engine.device}; it cannot be evaluated on "
+                                   f"{want} (build a second module, or pass bank= a PatchBank of that device)")
         if self._engine is None:
             if self._bank is None:
                 images, labels = dataset_to_tensors(self.dataset)
@@ -105,9 +110,19 @@ class _ScoreModuleBase(nn.Module):
         kind = kind or self.kind
         eng = self.engine()
         order = None
+        rank, world = self._rank_world()
         if self.shuffle or kind == "LS" and self._ls_shuffles():
             order = dataloader_shuffle_order(eng.bank.N)
-        rank, world = self._rank_world()
+            if world > 1:
+                # every rank must slice the SAME permutation: rank r takes order[r::world], so ranks whose global RNG
+                # states differ would otherwise count some images twice and drop others.  Rank 0's draw wins (each rank
+                # still consumes its own two RNG draws, as one reference evaluation does).
+                import torch.distributed as dist
+                t = torch.from_numpy(order.astype("int64"))
+                if dist.get_backend(self.process_group) == "nccl":
+                    t = t.to(eng.device)
+                dist.broadcast(t, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
+                order = t.cpu().numpy()
         return eng.bank.selection(kind, label, self.batch_size, self.max_samples, order, rank, world)
 
     def _ls_shuffles(self):
