@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("CDS_LIB_PATH", os.path.join(_HERE, "libcdscore.so")) 
 
 KIND = {"LS": 0, "ELS": 1, "bbELS": 2}
 PAD = {"zeros": 0, "circular": 1}
+ELS_VARIANT = {"auto": 0, "fma": 1, "v2": 1, "pv": 2}      # CDS_ELS_AUTO / _FMA / _PV
 
 _p = C.c_void_p
 _i = C.c_int
@@ -32,12 +33,10 @@ SIGNATURES = {
     "cds_ls_rows_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_bbels_edge_supported": (_i, [_i, _i, _i, _i]),
     "cds_bbels_edge_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
-    "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,
+    "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _i,
                                    _p, _p, _p, _p, _p]),
     "cds_els_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
-    "cds_els_partials_umma_pv": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i,
-                                      _p, _p, _p, _p, _p]),
-    "cds_els_umma_pv_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "cds_els_umma_pv_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "cds_combine": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "cds_combine_packed": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "cds_finalize": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

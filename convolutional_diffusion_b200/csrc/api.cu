@@ -12,7 +12,7 @@ void cds_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-extern "C" int cds_abi_version(void) { return 1; }
+extern "C" int cds_abi_version(void) { return 2; }
 extern "C" const char* cds_last_error(void) { return g_err; }
 
 extern "C" int cds_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -31,6 +31,18 @@
 //     columns per thread, so one 16-byte centre-pixel load per channel serves 16 pairs): (1) tcgen05.ld + 3-input max;
 //     a chunk whose best logit is 2^-40 below the running max for every row of the warp is skipped; (2) packed f32x2
 //     fma -> ex2 -> weighted sums.  Floor = 8 cycles per candidate column twice over (TMEM read bandwidth, MUFU).
+//   * P.V epilogue (template flag PV, single-plane banks): the weighted sum of the centre pixels is a second contraction on
+//     the tensor cores.  One sweep over the accumulators: tcgen05.ld (row per thread), row max, P = 2^(logit - m_ref + 8)
+//     packed to fp16 and stored IN PLACE over the consumed columns (tcgen05.st); the MMA warp then issues
+//     O[128 x 16] += P[128 x 16 candidates] . V'[16 candidates x 16] per 16-column chunk with P as the TMEM-resident A
+//     operand.  V' (centre pixels and a ones row, fp16, exact for 8-bit banks) is routed per chunk to the 4 O columns of
+//     the epilogue warpgroup that owns the chunk, so every (warpgroup, row) has a private reference m_ref and a private
+//     accumulator and nothing is exchanged per tile.  m_ref is not a running max: it is re-based on a fixed schedule
+//     (before image 1, 2, 4, 8, ... of the CTA's slice: drain O into the thread's fp32 state, m_ref = best logit seen);
+//     a chunk holding a logit more than 2^7.5 above m_ref (fp16 overflow) is evaluated exactly on the CUDA cores into the
+//     same fp32 state and stores P = 0, so the result never depends on how good the reference is -- only the speed does.
+//     Measured basis (profiles/r02_tmem_ld_floor.log): tcgen05.ld 32x32b delivers 700-800 B/clk/SM (the 16x256b shape
+//     250), MUFU.EX2 16/clk/SM, an N=16 UMMA ~29 clk.
 #include <type_traits>
 #include "umma_common.cuh"
 
@@ -45,7 +57,7 @@ __device__ unsigned long long g_els_counters[8];
 #endif
 
 // ------------------------------------------------------------------ the kernel
-template <int C>
+template <int C, bool PV>
 __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const UmmaGeom& g = p.g;
@@ -59,12 +71,13 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 
   uint8_t* sA = smem;
   uint8_t* sStage = smem + g.smem_A;
-  float* sMerge = reinterpret_cast<float*>(smem + g.smem_A + g.smem_stage);           // [NUM_EPI_WG-1][128][2+C]
+  float* sMerge = reinterpret_cast<float*>(sA);           // [NUM_EPI_WG-1][128][2+C], aliases the query tile (see make_geom)
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + g.smem_A + g.smem_stage + g.smem_merge + g.smem_table);
-  // barriers: full[2], empty[2], vready[2], tfull[2], tempty[2]; then the TMEM base address
+  // barriers: full[2], empty[2], vready[2], tfull[2], tempty[2] (P.V: pready[2]), pvdone[2]; then the TMEM base address
   const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 16, bar_vready = bar_full + 32;
-  const uint32_t bar_tfull = bar_full + 48, bar_tempty = bar_full + 64;
-  uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sBar + 10);
+  const uint32_t bar_tfull = bar_full + 48, bar_tempty = bar_full + 64, bar_pvdone = bar_full + 80;
+  const uint32_t bar_pready = bar_tempty, bar_vempty = bar_full + 96;
+  uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sBar + 14);
 
   const float beta = p.beta[b];
   const float a = sqrtf(1.f - beta);
@@ -74,12 +87,15 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   if (tid == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1 + 4 * NUM_EPI_WG);   // MMA commit + every epilogue warp
+      mbar_init(bar_empty + 8 * s, PV ? 1 + 2 : 1 + 4 * NUM_EPI_WG);   // MMA commit + every epilogue warp (P.V: + the two
+                                                                        // builder warps, the only other readers of a stage)
+      mbar_init(bar_vempty + 8 * s, 1);                   // P.V: commit after the band's last P.V releases its V' slot
       mbar_init(bar_vready + 8 * s, 2);                   // the two builder warps
     }
     for (int q = 0; q < 2; ++q) {
       mbar_init(bar_tfull + 8 * q, 1);
-      mbar_init(bar_tempty + 8 * q, 4 * NUM_EPI_WG);      // every epilogue warp reads every tile
+      mbar_init(bar_tempty + 8 * q, 4 * NUM_EPI_WG);      // every epilogue warp reads every tile (P.V: has stored its P)
+      mbar_init(bar_pvdone + 8 * q, 1);                   // P.V: commit after the P.V UMMAs of a tile
     }
     fence_barrier_init();
   }
@@ -164,6 +180,16 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 
   // ---- resident query slices: the first n_tmem K=16 slices of the A operand are copied into TMEM once (row q = lane q,
   // one column = two K elements), so those UMMAs stop re-reading 4 KB of shared memory per candidate tile
+  if (PV) {          // O accumulator starts at zero: every P.V accumulates
+    if (warp >= 4 && warp < 8) {
+      const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      tmem_st16(tmem_base + g.o_col + (((uint32_t)((warp & 3) * 32)) << 16), z);
+      tmem_st_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (g.n_tmem > 0) {
     if (warp >= 4 && warp < 8) {
       const int q = tid - 128;
@@ -226,6 +252,82 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     const uint32_t a_base = smem_u32(sA) >> 4;
     const int nm = g.n_mma, nt = g.n_tmem;
     const uint32_t a_tmem = tmem_base + g.a_tmem_col;
+    if constexpr (PV) {
+      // Issue order: S(0), S(1), P.V(0), S(2), P.V(1), ...  S(T+2) reuses the buffer of tile T and is issued after P.V(T),
+      // which itself waits until every epilogue warp has read S(T) and stored P(T) over it; tensor-core operations
+      // execute in issue order, so no barrier is needed between P.V(T) reading the buffer and S(T+2) overwriting it.
+      const int nvb = g.nvb, nck = g.G >> 1;              // 16-column chunks per tile (every band has N = 8*G columns)
+      const uint32_t idesc = (1u << 4) | (((uint32_t)(8 * g.G) >> 3) << 17) | ((128u >> 4) << 24);
+      // P.V instruction: D = f32, A = B = f16, K-major, N = 16, M = 128, K = 16
+      const uint32_t idesc_pv = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+      const int units = n_img * g.nchunks, total_tiles = units * nvb;
+      auto issue_pv = [&](int Tp) {
+        const int un = Tp / nvb, vb = Tp - un * nvb;
+        const int s = un & 1, buf = Tp & 1;
+        if (vb == 0) mbar_wait(bar_vready + 8 * s, (un >> 1) & 1, 7);          // V' operands of this band are built
+        mbar_wait(bar_pready + 8 * buf, (uint32_t)((Tp >> 1) & 1), 8);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_u32(sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes);
+          const uint32_t vbase = (st + g.v_data_off + (uint32_t)vb * g.v_tile_bytes) >> 4;
+          const uint32_t zpre = st >> 4, zpost = (st + g.v_zpost_off) >> 4;
+          const uint32_t s_col = tmem_base + buf * g.tmem_buf1, o_col = tmem_base + g.o_col;
+          const int rot = (Tp * nck) & 3;
+#ifdef CDS_PROFILE_SWITCHES
+          if (!(p.flags & 16))          // profiling: 16 = no P.V UMMAs
+#endif
+          for (int j = 0; j < nck; ++j) {
+            // chunk j = patch rows 2j, 2j+1 of the band = two 128-byte core matrices (8 V' rows x 8 candidates).  Its owner
+            // warpgroup w accumulates in O columns 4w..4w+3: for w < 2 the value rows are the first 8-row group of the
+            // operand and the second group is the zero block behind the data; for w >= 2 the first group is the zero block
+            // in front of the data and the value rows are the second group (SBO = distance between the groups).
+            const int w = (j + rot) & 3;
+            const uint32_t vj = vbase + 16u * j;
+            const uint32_t start = w < 2 ? vj : zpre, sbo = w < 2 ? zpost - vj : vj - zpre;
+            const uint64_t bd = (1ull << 46) | ((uint64_t)(sbo & 0x3FFFu) << 32) | (8ull << 16) | (uint64_t)(start & 0x3FFFu);
+            umma_f16_ts(o_col, s_col + 16 * j, bd, idesc_pv, 1u);
+          }
+          umma_commit(bar_pvdone + 8 * buf);
+          if (vb == nvb - 1) umma_commit(bar_vempty + 8 * s);                   // last reader of this V' slot
+        }
+        __syncwarp();
+      };
+      int T = 0;
+      for (int un = 0; un < units; ++un) {
+        const int s = un & 1;
+        const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
+        for (int vb = 0; vb < nvb; ++vb, ++T) {
+          if (T >= 2) issue_pv(T - 2);      // first: it may be the commit that releases the stage the next band waits for
+          if (vb == 0) {
+            mbar_wait(bar_full + 8 * s, (un >> 1) & 1, 2);
+            tc_fence_after();
+          }
+          const uint32_t d_tmem = tmem_base + (T & 1) * g.tmem_buf1;
+          const uint32_t b_base = (stage_addr + vb * 128u) >> 4;
+          if (elect_one()) {
+            int t = 0;
+#ifdef CDS_PROFILE_SWITCHES
+            if (p.flags & 8) t = nm;      // profiling: 8 = no main UMMAs (accumulators keep whatever they held)
+#endif
+#pragma unroll 4
+            for (; t < nt; ++t)
+              umma_f16_ts(d_tmem, a_tmem + 8 * t, b_hi | (uint64_t)(p.table[t].y + b_base), idesc, t ? 1u : 0u);
+#pragma unroll 4
+            for (; t < nm; ++t) {
+              const uint2 e = p.table[t];
+              umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, t ? 1u : 0u);
+            }
+            umma_commit(bar_tfull + 8 * (T & 1));
+            if (vb == nvb - 1) umma_commit(bar_empty + 8 * s);     // the stage's last main UMMAs: back to the producer
+          }
+          __syncwarp();
+        }
+      }
+      if (total_tiles >= 2) issue_pv(total_tiles - 2);
+      issue_pv(total_tiles - 1);
+      // nothing may still be executing on the tensor pipe when the CTA gives its TMEM back
+      mbar_wait(bar_pvdone + 8 * ((total_tiles - 1) & 1), (uint32_t)(((total_tiles - 1) >> 1) & 1), 10);
+    } else {
     long long T = 0;
     int unit = 0;
     for (int n = 0; n < n_img; ++n) {
@@ -269,11 +371,66 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         __syncwarp();
       }
     }
+    }
   } else if (warp == 2 || warp == 3) {
     // =========================== builders: centre pixels of every candidate of the staged image, in tile order:
     // tile (ch,vb), column r = 8*gr + rr <-> patch (u0+gr, 8*vb+rr); pairs of columns are stored side by side
     const int bt = tid - 64;   // 0..63
     int unit = 0;
+    if constexpr (PV) {
+      // V' operand of the P.V contraction: per tile and patch row (= 8 candidates) one 128-byte core matrix of 8 rows x 8
+      // fp16: rows 4*(w&1) + c = scale * centre pixel of channel c (the bank's own fp16 values), row 4*(w&1) + 3 = 1 (softmax
+      // denominator), everything else 0, where w is the warpgroup that owns the chunk; candidates that are not valid
+      // patches get all-zero columns, which is what masks them in the sums
+      const int nck = g.G >> 1;
+      for (int n = 0; n < n_img; ++n) {
+        for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+          const int s = unit & 1, u0 = g.chunk_u0[ch];
+          mbar_wait(bar_vempty + 8 * s, ((unit >> 1) & 1) ^ 1, 11);      // the band two before this one is done with the slot
+          mbar_wait(bar_full + 8 * s, (unit >> 1) & 1, 6);
+          const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
+          uint8_t* vd = sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes + g.v_data_off;
+          for (int item = bt; item < g.nvb * g.G; item += 64) {
+            const int vb = item / g.G, kg = item - vb * g.G;
+            const int T = unit * g.nvb + vb;
+            const int hs = ((kg >> 1) + T * nck) & 1;                 // owner & 1: which half of the 8 rows carries values
+            const int u = u0 + kg;
+            uint32_t rows[4][4];                                       // [channel / ones][4 x f16x2]
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rows[c][q] = 0u;
+            if (u < g.Ph) {
+#pragma unroll
+              for (int rr = 0; rr < 8; ++rr) {
+                const int v = 8 * vb + rr;
+                if (v < g.Pw) {
+#pragma unroll
+                  for (int c = 0; c < C; ++c) {
+                    const size_t go = ((size_t)(c * g.R + kg + g.d) * g.W + (v + g.d)) * 16;   // band-relative row
+                    const uint32_t h = *reinterpret_cast<const uint16_t*>(st + go);
+                    rows[c][rr >> 1] |= h << (16 * (rr & 1));
+                  }
+                  rows[3][rr >> 1] |= 0x3C00u << (16 * (rr & 1));      // 1.0 in fp16
+                }
+              }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(vd + (size_t)vb * g.v_tile_bytes + (size_t)kg * 128);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              dst[4 * hs + c] = make_uint4(rows[c][0], rows[c][1], rows[c][2], rows[c][3]);
+              dst[4 * (hs ^ 1) + c] = make_uint4(0, 0, 0, 0);
+            }
+          }
+          fence_proxy_async();           // generic-proxy writes above are read by the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar_vready + 8 * s);
+            mbar_arrive(bar_empty + 8 * s);   // done reading the stage
+          }
+        }
+      }
+    } else
     for (int n = 0; n < n_img; ++n) {
       for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
         const int s = unit & (S - 1);
@@ -314,10 +471,169 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     // serves 16 (query, candidate) pairs: a quarter of the shared-memory traffic of the row-per-thread 32x32b shape, and
     // shared-memory bandwidth (these loads + the UMMA operand reads) is what bounds the kernel.
     const int wg = (warp - 4) >> 2, lq = warp & 3;
-    const int t4 = lane & 3, tr = lane >> 2;
     const uint32_t lane_addr = ((uint32_t)(lq * 32)) << 16;
     const float c1 = CDS_LOG2E * a / beta * inv_scale;   // accumulator -> log2-unit logit
     const float2 c1c1 = make_float2(c1, c1);
+    // what both epilogues hand to the merge below: the softmax state of query row q over this warpgroup's columns
+    float m = -INFINITY, l = 0.f, acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    int q = 0;
+    if constexpr (PV) {
+      // ===== P.V epilogue: row per thread (32x32b fragment), one sweep, weights go back to TMEM as the fp16 A operand of
+      // the P.V contraction (see the file header).  st = this thread's fp32 state: everything drained from O so far plus
+      // the chunks that took the exact path.
+      q = 32 * lq + lane;
+      Softmax2<C> st;
+      st.init();
+      float m_ref = -INFINITY, m_seen = -INFINITY;
+      bool o_dirty = false;                               // warp uniform: P != 0 was stored since the last drain
+      const uint32_t o_addr = tmem_base + g.o_col + 4 * wg + lane_addr;
+      const int nvb = g.nvb, nck = g.G >> 1;
+#ifdef CDS_PROFILE_SWITCHES
+      unsigned cnt_chunks = 0, cnt_skipped = 0, cnt_exact = 0, cnt_drain = 0;
+#endif
+      // folds the O accumulator (reference m_ref) into st and clears it; every P.V issued so far must be complete, i.e.
+      // the commit after the P.V of tile Tcur-1 (all earlier ones complete before it: issue order)
+      auto drain = [&](uint32_t Tcur) {
+        const uint32_t Tp = Tcur - 1u;
+        mbar_wait(bar_pvdone + 8 * (Tp & 1u), (Tp >> 1) & 1u, 9);
+        tc_fence_after();
+        uint32_t o[4];
+        tmem_ld4(o_addr, o);
+        tmem_ld_wait4(o);
+        const float mb = m_ref - PV_SHIFT, lb = __uint_as_float(o[3]);
+        if (lb > 0.f) {
+          const float M = fmaxf(st.m, mb);
+          const float s0 = (st.m == -INFINITY) ? 0.f : ex2(st.m - M), s1 = ex2(mb - M);
+          st.l = st.l * s0 + lb * s1;
+#pragma unroll
+          for (int c = 0; c < C; ++c) st.acc[c] = st.acc[c] * s0 + __uint_as_float(o[c]) * inv_scale * s1;
+          st.m = M;
+        }
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        tmem_st4(o_addr, z);
+        tmem_st_wait_all();
+        o_dirty = false;
+      };
+      uint32_t T = 0;
+      int unit = 0;
+      for (int n = 0; n < n_img; ++n) {
+        const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
+        if (n > 0 && (n & (n - 1)) == 0) {                 // re-base the reference before image 1, 2, 4, 8, ...
+          if (o_dirty) {
+            drain(T);
+#ifdef CDS_PROFILE_SWITCHES
+            ++cnt_drain;
+#endif
+          }
+          m_ref = m_seen;
+        }
+        const float off = lw - m_ref + PV_SHIFT;           // +inf while there is no reference yet (then every chunk is exact)
+        const float2 off2 = make_float2(off, off);
+        for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
+          const int s = unit & 1;
+          for (int vb = 0; vb < nvb; ++vb, ++T) {
+            const uint32_t buf = T & 1u;
+            mbar_wait(bar_tfull + 8 * buf, (T >> 1) & 1u, 5);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * g.tmem_buf1 + lane_addr;
+            // an 8-column block that runs past the end of the image row aliases the next row's granules; for the band's last
+            // patch row those lie outside the staged norm-plane rows, so such columns carry no marker and could win the max
+            // (and with it the reference): mask them explicitly.  Images whose width is a multiple of 8 never get here.
+            const bool edge = 8 * vb + 8 > g.W;
+            const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - g.chunk_u0[ch];
+#ifdef CDS_PROFILE_SWITCHES
+            if (!(p.flags & 2))           // profiling: 2 = the epilogue touches nothing (tensor pipe + barriers only)
+#endif
+            for (int j = (int)((wg - T * nck) & 3u); j < nck; j += 4) {      // chunks owned by this warpgroup: (j + T*nck) % 4 == wg
+              uint32_t r[16];
+              tmem_ld16(taddr + 16 * j, r);
+              tmem_ld_wait16(r);
+              if (edge) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if ((e & 7) >= nval_v || 2 * j + (e >> 3) >= nval_u) r[e] = 0xff800000u;
+              }
+              float mx = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+#pragma unroll
+              for (int e = 3; e < 15; e += 2) mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+              mx = fmaxf(mx, __uint_as_float(r[15]));
+              const float lg = fmaf(mx, c1, lw);           // best logit of the chunk for this row (c1 > 0)
+              m_seen = fmaxf(m_seen, lg);
+              const float dd = lg - m_ref;
+              uint32_t pk[8];
+#ifdef CDS_PROFILE_SWITCHES
+              ++cnt_chunks;
+#endif
+              if (__all_sync(0xffffffffu, dd < -PV_SKIP)) {
+                // every weight of the chunk rounds to zero in fp16 (< 2^-33 of the reference, which never exceeds the best
+                // logit seen): up to 4.5e6 such candidates add < 6e-4 of one top candidate's weight
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = 0u;
+#ifdef CDS_PROFILE_SWITCHES
+                ++cnt_skipped;
+#endif
+#ifdef CDS_PROFILE_SWITCHES
+              } else if ((p.flags & 64) || __any_sync(0xffffffffu, !(dd <= PV_EXCEED))) {     // 64: every chunk exact
+#else
+              } else if (__any_sync(0xffffffffu, !(dd <= PV_EXCEED))) {
+#endif
+                // some weight would overflow fp16 (or there is no reference yet): exact online softmax on the CUDA cores
+                // for the 32 rows x 16 candidates of this warp, P = 0.  The V' block supplies centre pixels and validity.
+                mbar_wait(bar_vready + 8 * s, (unit >> 1) & 1, 4);
+                const uint8_t* vblk = sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes + g.v_data_off + (size_t)vb * g.v_tile_bytes +
+                                      (size_t)(2 * j) * 128 + (size_t)(4 * (wg & 1)) * 16;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const uint8_t* col = vblk + (e >> 3) * 128 + (e & 7) * 2;
+                  if (*reinterpret_cast<const uint16_t*>(col + 3 * 16) != 0) {          // valid candidate (ones row)
+                    float v[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) v[c] = __half2float(*reinterpret_cast<const __half*>(col + c * 16)) * inv_scale;
+                    st.push(fmaf(__uint_as_float(r[e]), c1, lw), v);
+                  }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = 0u;
+#ifdef CDS_PROFILE_SWITCHES
+                ++cnt_exact;
+#endif
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float2 ar = fma2(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), c1c1, off2);
+#ifdef CDS_PROFILE_SWITCHES
+                  if (p.flags & 32) { pk[e] = pack_f16x2(ar.x * 1e-3f, ar.y * 1e-3f); continue; }   // profiling: 32 = no MUFU
+#endif
+                  pk[e] = pack_f16x2(ex2(ar.x), ex2(ar.y));
+                }
+                o_dirty = true;
+              }
+              tmem_st8(taddr + 16 * j, pk);
+            }
+            tmem_st_wait_all();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(bar_pready + 8 * buf);
+          }
+        }
+      }
+      if (o_dirty) drain(T);
+      m = st.m;
+      l = st.l;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = st.acc[c];
+#ifdef CDS_PROFILE_SWITCHES
+      if (lane == 0) {
+        atomicAdd(&g_els_counters[0], (unsigned long long)cnt_chunks);
+        atomicAdd(&g_els_counters[1], (unsigned long long)cnt_skipped);
+        atomicAdd(&g_els_counters[5], (unsigned long long)cnt_exact);
+        atomicAdd(&g_els_counters[6], (unsigned long long)cnt_drain);
+      }
+#endif
+    } else {
+    const int t4 = lane & 3, tr = lane >> 2;
     // the norm-plane marker suppresses invalid positions by 2^-(log2e * a^2/(2 beta) * 3 * INVALID_NORM); when beta -> 1 that
     // factor fades (a -> 0), so fall back to explicit column masking
     const bool weak_marker = CDS_LOG2E * a * a / (2.f * beta) * 3.f * INVALID_NORM < 64.f;
@@ -513,9 +829,6 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 #endif
     // the four threads t4 = 0..3 of a row group hold the same four rows over disjoint columns: merge them with shuffles,
     // after which thread (tr, t4) owns row tr + 8*t4 of its warp's 32
-    float m = -INFINITY, l = 0.f, acc[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float M = fmaxf(m4[j], __shfl_xor_sync(0xffffffffu, m4[j], 1));
@@ -533,7 +846,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         if (t4 == j) acc[c] = aj;
       }
     }
-    const int q = 32 * lq + tr + 8 * t4;   // query row = TMEM lane
+    q = 32 * lq + tr + 8 * t4;   // query row = TMEM lane
+    }
     const int qi = i0 + (q >> 3), qj = j0 + (q & 7);
     // merge the warpgroups' partial softmax states and write this split's partials
     if (wg > 0) {
@@ -628,6 +942,12 @@ extern "C" int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passe
   return make_geom(C, H, W, k, passes, bank_planes, g, local) ? g.smem_total : 0;
 }
 
+extern "C" int cds_els_umma_pv_supported(int C, int H, int W, int k, int passes, int bank_planes) {
+  UmmaGeom g;
+  uint2 local[MAX_MMAS];
+  return make_geom(C, H, W, k, passes, bank_planes, g, local, 1) ? 1 : 0;
+}
+
 extern "C" int cds_pack_norm_plane(const float* images, int64_t N, int C, int H, int W, int k, void* out_f16,
                                    void* stream) {
   CDS_CHECK_ARG(N >= 1 && k >= 1 && k <= H && k <= W, "cds_pack_norm_plane: bad arguments");
@@ -639,36 +959,55 @@ extern "C" int cds_pack_norm_plane(const float* images, int64_t N, int C, int H,
   return CDS_OK;
 }
 
-extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
-                                     const void* bank_hi, const void* bank_lo, const void* bank_rows, float bank_scale,
-                                     const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
-                                     int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
-                                     void* stream) {
-  UmmaParams p;
-  const int planes = bank_lo ? 2 : 1;
-  // with a rows8 plane the trailing k % 8 patch rows are contracted as horizontal granules (fewer, fuller UMMAs);
-  // geometries that layout does not cover fall back to vertical granules only
-  const char* mx = getenv("CDS_ELS_MIXED");     // A/B switch: 0 = vertical granules only
-  const bool try_mixed = bank_rows != nullptr && !(mx && atoi(mx) == 0);
+namespace {
+// geometry for one epilogue variant: prefers the mixed K layout (rows8 plane) when it keeps the tiling and saves >= 8 %
+// of the UMMAs.  Measured on 32x32x3: k=17 8.5 -> 6.5 ms; k=9 with the band halved to fit shared memory was 12 % slower
+// although it issues 39 % fewer UMMAs.
+bool pick_geom(int C, int H, int W, int k, int passes, int planes, int pv, bool try_mixed, UmmaParams& p) {
   bool have = false;
   if (try_mixed) {
     UmmaGeom gv;
     static thread_local uint2 scratch[MAX_MMAS];
-    const bool okv = make_geom(C, H, W, k, passes, planes, gv, scratch) != 0;
-    const bool okm = make_geom(C, H, W, k, passes, planes, p.g, p.table, 0, 1) != 0;
-    // the mixed layout must keep the tiling (same band height and staging depth: the epilogue cost per image is then
-    // unchanged) and save at least 8 % of the UMMAs.  Measured on 32x32x3: k=17 8.5 -> 6.5 ms; k=9 with the band
-    // halved to fit shared memory was 12 % slower although it issues 39 % fewer UMMAs (epilogue bound).
+    const bool okv = make_geom(C, H, W, k, passes, planes, gv, scratch, pv) != 0;
+    const bool okm = make_geom(C, H, W, k, passes, planes, p.g, p.table, pv, 1) != 0;
     have = okm && (!okv || (p.g.stages >= gv.stages && p.g.G == gv.G && p.g.n_mma * 100 < gv.n_mma * 92));
   }
-  if (!have && !make_geom(C, H, W, k, passes, planes, p.g, p.table)) {
+  return have || make_geom(C, H, W, k, passes, planes, p.g, p.table, pv) != 0;
+}
+}  // namespace
+
+extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
+                                     const void* bank_hi, const void* bank_lo, const void* bank_rows, float bank_scale,
+                                     const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
+                                     int splits, int passes, int variant, float* m, float* l, float* acc, float* dbg_dots,
+                                     void* stream) {
+  UmmaParams p;
+  const int planes = bank_lo ? 2 : 1;
+  const char* mx = getenv("CDS_ELS_MIXED");     // A/B switch: 0 = vertical granules only
+  const bool try_mixed = bank_rows != nullptr && !(mx && atoi(mx) == 0);
+  CDS_CHECK_ARG(variant >= CDS_ELS_AUTO && variant <= CDS_ELS_PV, "cds_els_partials_umma: unknown variant %d", variant);
+  // P.V epilogue: single-plane banks, no dot-product dump.  "auto" uses it where it was measured faster: up to k = 13 the
+  // kernel is bound by the epilogue (MUFU + issue slots); from k = 15 by the main contraction, where the extra N=16 UMMAs
+  // of the P.V contraction cost more than the FMA-pipe weighted sum they replace.
+  bool pv = false;
+  if (variant != CDS_ELS_FMA && dbg_dots == nullptr) {
+    const char* pk = getenv("CDS_PV_MAX_K");    // A/B switch for the auto rule
+    const int pv_max_k = pk ? atoi(pk) : 13;
+    if (variant == CDS_ELS_PV || k <= pv_max_k) pv = pick_geom(C, H, W, k, passes, planes, 1, try_mixed, p);
+  }
+  if (variant == CDS_ELS_PV && !pv) {
+    cds_set_error("cds_els_partials_umma: the P.V epilogue does not support C=%d H=%d W=%d k=%d passes=%d planes=%d%s", C, H,
+                  W, k, passes, planes, dbg_dots ? " with a dot-product dump" : "");
+    return CDS_ERR_UNSUPPORTED;
+  }
+  if (!pv && !pick_geom(C, H, W, k, passes, planes, 0, try_mixed, p)) {
     cds_set_error("cds_els_partials_umma: unsupported geometry C=%d H=%d W=%d k=%d passes=%d planes=%d", C, H, W, k,
                   passes, planes);
     return CDS_ERR_UNSUPPORTED;
   }
   if (getenv("CDS_DEBUG_GEOM"))
-    fprintf(stderr, "cdscore: els_umma k=%d passes=%d planes=%d mixed=%d G=%d chunks=%d nvb=%d n_mma=%d n_tmem=%d stages=%d smem=%d\n",
-            k, passes, planes, p.g.rem ? 1 : 0, p.g.G, p.g.nchunks, p.g.nvb, p.g.n_mma, p.g.n_tmem, p.g.stages, p.g.smem_total);
+    fprintf(stderr, "cdscore: els_umma k=%d passes=%d planes=%d pv=%d mixed=%d G=%d chunks=%d nvb=%d n_mma=%d n_tmem=%d stages=%d smem=%d\n",
+            k, passes, planes, pv ? 1 : 0, p.g.rem ? 1 : 0, p.g.G, p.g.nchunks, p.g.nvb, p.g.n_mma, p.g.n_tmem, p.g.stages, p.g.smem_total);
   CDS_CHECK_ARG(B >= 1 && n_sel >= 1 && splits >= 1, "cds_els_partials_umma: empty problem");
   if (splits > n_sel) splits = (int)n_sel;
   p.B = B; p.pad = query_pad; p.splits = splits; p.n_sel = n_sel;
@@ -689,10 +1028,15 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
   dim3 grid(tiles, splits, B);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-#define LAUNCH(CC)                                                                                                  \
-  case CC:                                                                                                          \
-    e = cudaFuncSetAttribute(els_umma_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g.smem_total);     \
-    if (e == cudaSuccess) els_umma_kernel<CC><<<grid, THREADS, p.g.smem_total, st>>>(p);                            \
+#define LAUNCH(CC)                                                                                                        \
+  case CC:                                                                                                                \
+    if (pv) {                                                                                                             \
+      e = cudaFuncSetAttribute(els_umma_kernel<CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g.smem_total);   \
+      if (e == cudaSuccess) els_umma_kernel<CC, true><<<grid, THREADS, p.g.smem_total, st>>>(p);                          \
+    } else {                                                                                                              \
+      e = cudaFuncSetAttribute(els_umma_kernel<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g.smem_total);  \
+      if (e == cudaSuccess) els_umma_kernel<CC, false><<<grid, THREADS, p.g.smem_total, st>>>(p);                         \
+    }                                                                                                                     \
     break;
   switch (C) {
     LAUNCH(1) LAUNCH(2) LAUNCH(3)

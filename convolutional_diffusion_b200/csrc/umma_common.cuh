@@ -18,6 +18,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int MAX_MMAS = 320;
 constexpr float SKIP_LOG2 = 40.f;        // chunks whose weights are all < 2^-40 of the running max are skipped
 constexpr float INVALID_NORM = 60000.f;  // norm-plane marker of positions that are not valid patches
+// P.V epilogue (weights as an fp16 tensor-core operand): P = 2^(logit - m_ref + PV_SHIFT)
+constexpr float PV_SHIFT = 8.f;          // weights down to 2^-22 of the reference stay normal fp16 numbers, down to 2^-33 nonzero
+constexpr float PV_EXCEED = 7.5f;        // a logit more than this above the reference would overflow fp16 -> exact SIMT path
+constexpr float PV_SKIP = 33.f;          // every logit of a chunk more than this below the reference: P rounds to 0 anyway
 
 struct UmmaGeom {
   int C, H, W, k, d, Ph, Pw;
@@ -39,6 +43,16 @@ struct UmmaGeom {
   int vt_tile;        // floats per tile of that table: per 16-column chunk and channel 16 floats in fragment order; PV variant: the
                       // fp32 (tf32) UMMA operand V'^T [16 rows][N] K-major = N*64 bytes per tile
   int pv;             // 1 = geometry of the P.V (weighted sum on the tensor cores) variant
+  int o_col;          // P.V: TMEM column of the O accumulator (16 columns: 4 per epilogue warpgroup = C sums + denominator)
+  // P.V: the V' operand lives in its own two-slot ring behind the stages (slot = band & 1), so that a stage can go back
+  // to the producer as soon as the main UMMAs of its band are done, while V' stays until the band's last P.V (one tile
+  // later).  Slot layout: 256 zero bytes, per tile and patch row one 128-byte core matrix (8 rows x 8 candidates fp16),
+  // 256 zero bytes.
+  int v_ring_off;     // offset of slot 0 from the first stage
+  int v_slot_bytes;
+  int v_data_off;     // offset of the operand blocks inside a slot (= 256)
+  int v_tile_bytes;   // bytes of V' per tile = G * 128
+  int v_zpost_off;    // offset of the trailing zero block inside a slot
   int stage_bytes;
   int stages;
   int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
@@ -170,6 +184,33 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait4(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// two fp32 -> one packed f16x2 register (lo = first argument = the lower K index of a TMEM-resident A operand)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 // packed fp32x2 arithmetic (sm_100+): two FMAs per issue slot
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   float2 d;
@@ -247,7 +288,8 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
                      int mixed = 0) {
   if (C < 1 || C > 3 || H > 64 || W > 64 || H < k || W < k || (k & 1) == 0 || k < 3) return 0;
   if (passes < 1 || passes > 2 || bank_planes < 1 || bank_planes > 2) return 0;
-  if (mixed && (pv || bank_planes > 1 || k < 9 || (k & 7) == 0)) return 0;
+  if (mixed && (bank_planes > 1 || k < 9 || (k & 7) == 0)) return 0;
+  if (pv && bank_planes > 1) return 0;          // the value operand of the P.V contraction is the single exact fp16 plane
   g.C = C; g.H = H; g.W = W; g.k = k; g.d = k / 2;
   g.Ph = H - k + 1; g.Pw = W - k + 1;
   g.nb = mixed ? k / 8 : (k + 7) / 8;
@@ -267,8 +309,11 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.nvb = (g.Pw + 7) / 8;
   g.pv = pv;
   g.smem_A = (g.a_bytes + 1023) / 1024 * 1024;
-  g.smem_merge = ((NUM_EPI_WG - 1) * 128 * 5 * 4 + 127) / 128 * 128;
-  g.smem_bar = 8 * 10 + 16 + 32;
+  // the merge scratch of the warpgroups' final states ([NUM_EPI_WG-1][128][2+C] floats) aliases the query tile: by then
+  // every UMMA that reads the tile has completed (each epilogue warp has waited for the last accumulator tile)
+  g.smem_merge = 0;
+  if (g.a_bytes < (NUM_EPI_WG - 1) * 128 * (2 + C) * 4) return 0;
+  g.smem_bar = 8 * 16 + 16 + 32;
   const int n_gran = C * g.nb * k;
   const int nm_max = (passes + bank_planes - 1) * ((n_gran + 2) / 2 + (C * g.rem * g.nbh + 1) / 2);
   if (nm_max > MAX_MMAS) return 0;
@@ -285,13 +330,14 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
     if (G > ((g.Ph + 1) & ~1)) continue;
     const int nch = (g.Ph + G - 1) / G;
     if (nch > MAX_CHUNKS || nch * G > H) continue;          // norm-plane / strip rows of a partial last band must exist
-    if (pv && 8 * G > 192) continue;                        // P.V variant: two S buffers + 2 x 4 O tiles of 16 columns in TMEM
+    if (pv && 16 * G + 16 > TMEM_COLS) continue;            // P.V variant: two S buffers + the 16-column O accumulator
     const int R = G + halo;
     const int band = C * R * g.S1;
     const int hband = g.rem ? C * (G + g.rem - 1) * g.S1 + g.tile_pad : 0;
-    const int vt_tile = pv ? 8 * G * 16 : 8 * G / 2 * 6;
+    const int vt_tile = pv ? 0 : 8 * G / 2 * 6;            // floats per tile of the centre-pixel table (FMA epilogue)
+    const int vring = pv ? 2 * ((512 + g.nvb * G * 128 + 127) / 128 * 128) : 0;
     const int stage = (bank_planes * (band + g.tile_pad) + hband + G * g.S1 + g.tile_pad + g.nvb * vt_tile * 4 + 127) / 128 * 128;
-    const int st = fixed + 2 * stage <= 227 * 1024 ? 2 : (fixed + stage <= 227 * 1024 ? 1 : 0);
+    const int st = fixed + vring + 2 * stage <= 227 * 1024 ? 2 : (fixed + vring + stage <= 227 * 1024 ? 1 : 0);
     // prefer two stages, then the cheapest tiling: candidate columns per image incl. padded patch rows, plus a fixed
     // per-tile overhead worth ~32 columns (barrier round trips, pipeline fill)
     const int waste = nch * (8 * G + 32);
@@ -308,7 +354,11 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.hb_off = bank_planes * (g.img_bytes + g.tile_pad);
   g.np_off = g.hb_off + (g.rem ? C * g.Rh * g.S1 + g.tile_pad : 0);
   g.vt_off = g.np_off + g.np_bytes + g.tile_pad;
-  g.vt_tile = pv ? 8 * g.G * 16 : 8 * g.G / 2 * 6;          // floats per tile (see UmmaGeom::vt_tile)
+  g.vt_tile = pv ? 0 : 8 * g.G / 2 * 6;                     // floats per tile (see UmmaGeom::vt_tile)
+  g.v_tile_bytes = g.G * 128;
+  g.v_data_off = 256;
+  g.v_zpost_off = g.v_data_off + g.nvb * g.v_tile_bytes;
+  g.v_slot_bytes = pv ? (g.v_zpost_off + 256 + 127) / 128 * 128 : 0;
   g.stage_bytes = (g.vt_off + g.nvb * g.vt_tile * 4 + 127) / 128 * 128;
   g.stages = bestStages;
 
@@ -352,12 +402,14 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.n_mma = nm;
   // TMEM: two accumulator buffers of 8*G columns; what is left holds query K slices, which the tensor core then reads
   // from TMEM instead of re-reading them from shared memory for every candidate tile
-  g.tmem_buf1 = pv ? 256 : 8 * g.G;
-  g.a_tmem_col = 2 * g.tmem_buf1;
-  g.n_tmem = pv ? 0 : (TMEM_COLS - g.a_tmem_col) / 8;
+  g.tmem_buf1 = 8 * g.G;
+  g.o_col = 2 * g.tmem_buf1;
+  g.a_tmem_col = 2 * g.tmem_buf1 + (pv ? 16 : 0);
+  g.n_tmem = (TMEM_COLS - g.a_tmem_col) / 8;
   if (g.n_tmem > nm) g.n_tmem = nm;
   if (g.n_tmem < g.n_h) return 0;                            // the horizontal slices have no shared-memory copy
-  g.smem_stage = g.stages * g.stage_bytes;
+  g.v_ring_off = g.stages * g.stage_bytes;
+  g.smem_stage = g.stages * g.stage_bytes + 2 * g.v_slot_bytes;
   g.smem_total = fixed + g.smem_stage;
   return g.smem_total <= 227 * 1024;
 }

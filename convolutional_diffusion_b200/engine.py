@@ -47,9 +47,11 @@ class ScoreEngine:
         self.precision = precision
         self.use_tensor_cores = use_tensor_cores
         self.group = group                       # torch.distributed process group for bank sharding (or None)
-        # ELS tensor-core kernel: "v2" = weighted sum on the FMA pipe (default, faster as measured in round 1),
-        # "pv" = weighted sum as a second UMMA (csrc/els_umma_pv.cu); CDS_ELS_VARIANT overrides for A/B runs
-        self.els_variant = os.environ.get("CDS_ELS_VARIANT", "v2")
+        # epilogue of the ELS tensor-core kernel: "auto" (P.V contraction on the tensor cores where supported and measured
+        # faster, k <= 13), "fma" (weighted sum on the FMA pipe), "pv" (P.V wherever supported); CDS_ELS_VARIANT overrides
+        self.els_variant = os.environ.get("CDS_ELS_VARIANT", "auto")
+        if self.els_variant not in _lib.ELS_VARIANT:
+            raise ValueError(f"CDS_ELS_VARIANT must be one of {sorted(_lib.ELS_VARIANT)}, got {self.els_variant!r}")
         self._buf = {}
         self.launches = 0                        # kernels launched through this engine (bench bookkeeping)
 
@@ -190,14 +192,14 @@ class ScoreEngine:
         S = self._splits(tiles, B, n_sel)
         P = self._partials(tag, S, B)
         planes = 1 if lo is None else 2
-        tail = (_lib.ptr(pn), _lib.ptr(idx), _lib.ptr(logw), n_sel, S, passes, _lib.ptr(P.m), _lib.ptr(P.l),
-                _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr())
-        head = (_lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(hi), _lib.ptr(lo))
-        if self.els_variant == "pv" and self.lib.cds_els_umma_pv_smem_bytes(b.C, b.H, b.W, k, passes, planes) > 0:
-            _lib.check(self.lib.cds_els_partials_umma_pv(*head, scale, *tail), "cds_els_partials_umma_pv")
-        else:
-            rows = b.rows8() if (k > 8 and k % 8) else None        # mixed K layout for the trailing k % 8 patch rows
-            _lib.check(self.lib.cds_els_partials_umma(*head, _lib.ptr(rows), scale, *tail), "cds_els_partials_umma")
+        variant = _lib.ELS_VARIANT[self.els_variant]
+        if variant == 2 and (dbg is not None or not self.lib.cds_els_umma_pv_supported(b.C, b.H, b.W, k, passes, planes)):
+            variant = 1                                            # "pv" means: wherever the geometry allows it
+        rows = b.rows8() if (k > 8 and k % 8) else None            # mixed K layout for the trailing k % 8 patch rows
+        _lib.check(self.lib.cds_els_partials_umma(
+            _lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(rows),
+            scale, _lib.ptr(pn), _lib.ptr(idx), _lib.ptr(logw), n_sel, S, passes, variant, _lib.ptr(P.m), _lib.ptr(P.l),
+            _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr()), "cds_els_partials_umma")
         self.launches += 1
         return P
 

@@ -98,21 +98,22 @@ int cds_bbels_edge_partials(const float* x, int B, int C, int H, int W, int k, c
  * 8-bit banks).  bank_lo may be NULL (8-bit-exact bank).  bank_rows may be NULL; when given (the plane = 2 output of
  * cds_pack_strip8: 8-pixel HORIZONTAL strips) and k > 8, k % 8 != 0, the trailing k % 8 patch rows are contracted
  * as horizontal granules instead of one more mostly-empty block of 8 rows (k = 9: 17 UMMAs per tile instead of 28).
- * dbg_dots: optional [B][H*W][P] raw dot dump of the first selected image (tests only, may be NULL). */
+ * dbg_dots: optional [B][H*W][P] raw dot dump of the first selected image (tests only, may be NULL).
+ * variant selects the epilogue (idealscore.py:456-471: softmax weights and the weighted sum of patch centres):
+ *   CDS_ELS_FMA  weights and weighted sums on the FMA pipe (any bank);
+ *   CDS_ELS_PV   single sweep, the weights go back to TMEM as an fp16 operand and the weighted sum is a second
+ *                contraction O += P.V' on the tensor cores (single-plane banks; error if the geometry is unsupported);
+ *   CDS_ELS_AUTO P.V where it is supported and was measured faster (k <= 13), else FMA. */
+#define CDS_ELS_AUTO 0
+#define CDS_ELS_FMA  1
+#define CDS_ELS_PV   2
 int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k,
                           const float* beta, const void* bank_hi, const void* bank_lo, const void* bank_rows,
                           float bank_scale, const void* norm_plane, const int32_t* idx, const float* logw,
-                          int64_t n_sel, int splits, int passes, float* m, float* l, float* acc,
+                          int64_t n_sel, int splits, int passes, int variant, float* m, float* l, float* acc,
                           float* dbg_dots, void* stream);
-/* Same contract, "P.V" variant: the weighted sum of the centre pixels also runs on the tensor cores (P is written
- * back to TMEM as fp16 and contracted with the per-tile value operand by a second UMMA).  Needs N <= 240 candidates
- * per accumulator tile and two shared-memory stages; cds_els_umma_pv_smem_bytes() == 0 means use the variant above. */
-int cds_els_partials_umma_pv(int query_pad, const float* x, int B, int C, int H, int W, int k,
-                             const float* beta, const void* bank_hi, const void* bank_lo, float bank_scale,
-                             const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
-                             int splits, int passes, float* m, float* l, float* acc, float* dbg_dots,
-                             void* stream);
-int64_t cds_els_umma_pv_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes);
+/* 1 when the P.V epilogue supports the geometry */
+int cds_els_umma_pv_supported(int C, int H, int W, int k, int passes, int bank_planes);
 /* dynamic shared memory the umma kernel needs for this geometry (0 = unsupported geometry) */
 int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes);
 

@@ -19,7 +19,7 @@ def main():
     P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
     lib.cds_pack_strip8.argtypes = [P, L, I, I, I, F, I, P, P]
     lib.cds_pack_norm_plane.argtypes = [P, L, I, I, I, I, P, P]
-    lib.cds_els_partials_umma.argtypes = [I, P, I, I, I, I, I, P, P, P, P, F, P, P, P, L, I, I, P, P, P, P, P]
+    lib.cds_els_partials_umma.argtypes = [I, P, I, I, I, I, I, P, P, P, P, F, P, P, P, L, I, I, I, P, P, P, P, P]
     lib.cds_combine.argtypes = [P, P, P, I, I, I, I, P, P, P, P]
     lib.cds_finalize.argtypes = [P, P, P, P, P, I, I, I, I, I, I, P, P, P]
     lib.cds_last_error.restype = ctypes.c_char_p
@@ -55,7 +55,7 @@ def main():
         l = torch.zeros_like(m)
         acc = torch.zeros(S, B, C, H * W, device="cuda")
         ok(lib.cds_els_partials_umma(1, ptr(x), B, C, H, W, k, ptr(beta), ptr(strip), None, ptr(rows), 255.0, ptr(pn),
-                                     ptr(idx), ptr(logw), n_sel, S, 2, ptr(m), ptr(l), ptr(acc), None, stream))
+                                     ptr(idx), ptr(logw), n_sel, S, 2, 0, ptr(m), ptr(l), ptr(acc), None, stream))
         ok(lib.cds_combine(ptr(m), ptr(l), ptr(acc), S, B, C, H * W, ptr(m), ptr(l), ptr(acc), stream))
         score = torch.empty_like(x)
         ok(lib.cds_finalize(ptr(x), ptr(beta), ptr(m), ptr(l), ptr(acc), B, C, H, W, 0, 0, None, ptr(score), stream))

@@ -31,7 +31,19 @@ def main():
     lib = _lib.load()
     have_counters = hasattr(lib, "cds_debug_els_counters")
     x0 = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(10_000)).cuda()
-    _, rec = machine.trajectory(x0, label=torch.tensor([label]), device="cuda")
+    cache = os.environ.get("CDS_TRAJ_CACHE")        # profiling switches corrupt the trajectory: take x from a clean run
+    if cache and os.path.isfile(cache):
+        rec = torch.load(cache)
+        for r in rec:
+            r["x"] = r["x"].cuda()
+    else:
+        _, rec = machine.trajectory(x0, label=torch.tensor([label]), device="cuda")
+        if cache:
+            torch.save([dict(i=r["i"], k=r["k"], beta=r["beta"], x=r["x"].cpu()) for r in rec], cache)
+    only = os.environ.get("CDS_STEPS")
+    if only:
+        keep = {int(v) for v in only.split(",")}
+        rec = [r for r in rec if r["i"] in keep]
     print(f"# n_sel={sel[2]} B={B} counters={'yes' if have_counters else 'no'}")
     print("# i k beta a/beta passes ms pairs/s TFLOP/s chunk_skip% warp_tile_skip% newmax%")
     tot = 0.0
@@ -59,7 +71,8 @@ def main():
         if have_counters:
             lib.cds_debug_els_counters(cnt)
             c = [int(v) for v in cnt]
-            extra = f" {100.0 * c[1] / max(c[0], 1):.1f} {100.0 * c[4] / max(c[3], 1):.1f} {100.0 * c[2] / max(c[0], 1):.2f}"
+            extra = (f" {100.0 * c[1] / max(c[0], 1):.1f} {100.0 * c[4] / max(c[3], 1):.1f} {100.0 * c[2] / max(c[0], 1):.2f}"
+                     f" exact%={100.0 * c[5] / max(c[0], 1):.3f} drains={c[6]}")
         print(f"{r['i']:2d} {k:2d} {beta_val:.5f} {((1 - beta_val) ** 0.5) / beta_val:7.2f} {passes} {ms:7.3f} "
               f"{pairs / ms * 1e3:.3e} {pairs * 2 * k * k * 3 / ms * 1e-9:7.1f}{extra}")
     print(f"# sum of the 19 evaluations: {tot:.2f} ms")

@@ -89,7 +89,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     loaded = _lib.load()
-    assert loaded.cds_abi_version() == 1
+    assert loaded.cds_abi_version() == 2
     # geometry query is host-only arithmetic: CIFAR shape, k=17, two query passes fits in 227 KB
     assert 0 < loaded.cds_els_umma_smem_bytes(3, 32, 32, 17, 2, 1) <= 227 * 1024
     assert 0 < loaded.cds_els_umma_smem_bytes(3, 64, 64, 17, 1, 1) <= 227 * 1024    # 64x64: staged in row bands
@@ -97,10 +97,9 @@ def test_library_exports_every_declared_symbol():
     assert loaded.cds_els_umma_smem_bytes(3, 32, 32, 4, 1, 1) == 0       # even kernel sizes are rejected
 
 
-def test_umma_geometry_choices():
-    """Host-side tiling decisions of the tensor-core kernel (printed with CDS_DEBUG_GEOM; the launch itself fails
-    without a GPU): CIFAR shape, one query pass.  The mixed K layout must keep the band height of the vertical layout
-    and is taken for k = 9, 11, 13, 17 (17/28, 26/34, 35/40, 57/77 UMMAs per tile) but not for k = 15 (44/46)."""
+def _umma_geometries(ks, variant, passes=1):
+    """Runs the geometry selection of cds_els_partials_umma (printed with CDS_DEBUG_GEOM) in a subprocess without a
+    GPU: the launch itself fails, the pointers are dummies."""
     import subprocess
     import sys
     code = (
@@ -109,25 +108,54 @@ def test_umma_geometry_choices():
         "from convolutional_diffusion_b200 import _lib\n"
         "lib = _lib.load()\n"
         "one = ctypes.c_void_p(16)\n"
-        "for k in (5, 9, 11, 13, 15, 17):\n"
-        "    lib.cds_els_partials_umma(1, None, 4, 3, 32, 32, k, None, None, None, one, 255.0, None, None, None, 100, 9, 1,\n"
-        "                              None, None, None, None, None)\n" % ROOT)
-    env = dict(os.environ, CDS_DEBUG_GEOM="1", CUDA_VISIBLE_DEVICES="")      # never launch: the pointers are dummies
+        "for k in %r:\n"
+        "    lib.cds_els_partials_umma(1, None, 4, 3, 32, 32, k, None, None, None, one, 255.0, None, None, None, 100, 9, %d,\n"
+        "                              %d, None, None, None, None, None)\n" % (ROOT, tuple(ks), passes, variant))
+    env = dict(os.environ, CDS_DEBUG_GEOM="1", CUDA_VISIBLE_DEVICES="")
     env.pop("CDS_ELS_MIXED", None)
+    env.pop("CDS_PV_MAX_K", None)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     geo = {}
     for line in r.stderr.splitlines():
-        m = re.search(r"els_umma k=(\d+) .* mixed=(\d) G=(\d+) chunks=(\d+) nvb=(\d+) n_mma=(\d+) n_tmem=(\d+) stages=(\d+) smem=(\d+)", line)
+        m = re.search(r"els_umma k=(\d+) .* pv=(\d) mixed=(\d) G=(\d+) chunks=(\d+) nvb=(\d+) n_mma=(\d+) n_tmem=(\d+) stages=(\d+) smem=(\d+)", line)
         if m:
             v = [int(g) for g in m.groups()]
-            geo[v[0]] = dict(mixed=v[1], G=v[2], chunks=v[3], nvb=v[4], n_mma=v[5], n_tmem=v[6], stages=v[7], smem=v[8])
-    assert set(geo) == {5, 9, 11, 13, 15, 17}, (r.stderr[-500:], r.stdout[-200:])
-    assert [geo[k]["mixed"] for k in (5, 9, 11, 13, 15, 17)] == [0, 1, 1, 1, 0, 1]
-    assert [geo[k]["n_mma"] for k in (5, 9, 11, 13, 15, 17)] == [8, 17, 26, 35, 46, 57]
-    assert [geo[k]["G"] for k in (5, 9, 11, 13, 15, 17)] == [28, 24, 22, 20, 18, 16]       # one band = all patch rows
+            geo[v[0]] = dict(pv=v[1], mixed=v[2], G=v[3], chunks=v[4], nvb=v[5], n_mma=v[6], n_tmem=v[7], stages=v[8], smem=v[9])
+    assert set(geo) == set(ks), (r.stderr[-500:], r.stdout[-200:])
+    return geo
+
+
+def test_umma_geometry_choices():
+    """Host-side tiling decisions of the tensor-core kernel, FMA-pipe epilogue: CIFAR shape, one query pass.  The mixed K
+    layout must keep the band height of the vertical layout and is taken for k = 9, 11, 13, 17 (17/28, 26/34, 35/40,
+    57/77 UMMAs per tile) but not for k = 15 (44/46)."""
+    ks = (5, 9, 11, 13, 15, 17)
+    geo = _umma_geometries(ks, variant=1)
+    assert [geo[k]["pv"] for k in ks] == [0] * 6
+    assert [geo[k]["mixed"] for k in ks] == [0, 1, 1, 1, 0, 1]
+    assert [geo[k]["n_mma"] for k in ks] == [8, 17, 26, 35, 46, 57]
+    assert [geo[k]["G"] for k in ks] == [28, 24, 22, 20, 18, 16]       # one band = all patch rows
     for k, g in geo.items():
         assert g["stages"] == 2 and g["chunks"] == 1 and g["smem"] <= 227 * 1024, (k, g)
         assert 16 * g["G"] + 8 * g["n_tmem"] <= 512, (k, g)                              # TMEM columns
+
+
+def test_umma_pv_geometry_choices():
+    """The same for the P.V epilogue (both query-pass counts): same bands and UMMA counts as the FMA epilogue, two stages
+    (the stage of a band is released one tile late), the 16-column O accumulator fits next to the two S buffers; "auto"
+    takes P.V up to k = 13 and the FMA epilogue above."""
+    ks = (3, 5, 7, 9, 11, 13, 15, 17)
+    for passes in (1, 2):
+        geo = _umma_geometries(ks, variant=2, passes=passes)
+        ref = _umma_geometries(ks, variant=1, passes=passes)
+        for k in ks:
+            g = geo[k]
+            assert g["pv"] == 1 and g["stages"] == 2 and g["smem"] <= 227 * 1024, (k, passes, g)
+            assert (g["G"], g["chunks"], g["nvb"], g["n_mma"], g["mixed"]) == \
+                (ref[k]["G"], ref[k]["chunks"], ref[k]["nvb"], ref[k]["n_mma"], ref[k]["mixed"]), (k, passes, g, ref[k])
+            assert 16 * g["G"] + 16 + 8 * g["n_tmem"] <= 512, (k, g)
+    auto = _umma_geometries(ks, variant=0)
+    assert [auto[k]["pv"] for k in ks] == [1, 1, 1, 1, 1, 1, 0, 0]
 
 
 def test_label_groups():
