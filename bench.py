@@ -235,22 +235,28 @@ def run_ours(args, scales):
         lab = 0
         sel = mod.selection(lab)
         n_c_local = sel[2]
-        x = xs_dev[0]
+        # every evaluation at its own noise level AND on the x the sampler actually feeds it at that step (an eager
+        # trajectory records them): the pass count depends on the noise level, the fraction of chunks that carry no weight
+        # on how close x is to the bank -- x = randn at a low noise level would be far cheaper than the real step
+        _, rec = machine.trajectory(xs_dev[0], label=torch.tensor([lab]), device=dev)
+        x_at = {r["i"]: r["x"].contiguous() for r in rec}
         tot_ms = tot_fl = 0.0
         per_eval = {}
-        for i in range(1, len(scales)):          # every evaluation at its own noise level (the pass count depends on it)
+        for i in range(1, len(scales)):
             k = scales[i]
+            x = x_at[i]
             beta_val = float(cosine_noise_schedule(torch.tensor([i / len(scales)])))
             beta = torch.full((B,), beta_val, device=dev)
             passes = eng.passes_for(k, beta_val)
+            aob = eng._a_over_beta(beta_val)
             for _ in range(2):
-                eng.umma_partials("circular", x, beta, k, sel, passes)
+                eng.umma_partials("circular", x, beta, k, sel, passes, a_over_beta=aob)
             reps = 3
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             a.record()
             for _ in range(reps):
-                eng.umma_partials("circular", x, beta, k, sel, passes)
+                eng.umma_partials("circular", x, beta, k, sel, passes, a_over_beta=aob)
             b_.record()
             torch.cuda.synchronize()
             per_eval.setdefault(k, []).append((a.elapsed_time(b_) / reps, passes))
@@ -271,7 +277,10 @@ def run_ours(args, scales):
                 # at batch 4, class 0, k=17: 712 MB; k=5: 621 MB, k=11: 917 MB); algorithmic = class sub-bank strip8 + norm
                 # plane + the rows8 rows of the mixed K layout once = 446 MB at k=17 (324 MB at k <= 7)
                 "traffic": 712.0e6, "traffic_algorithmic": 446.0e6,
-                "note": "algorithmic 2*k*k*C FLOP per (query, patch) pair, FLOP-weighted over the 19 evaluations of one "
+                "traffic_source": "ncu --set full capture of round 1 at batch 4, class 0, k=17 (profiles/r01g_els_umma_ncu_summary.md); "
+                                  "not re-measured by this run",
+                "note": "algorithmic 2*k*k*C FLOP per (query, patch) pair, FLOP-weighted over the 19 evaluations of one trajectory, each "
+                        "on the x of its own step; "
                         "trajectory; CUDA events around the kernel launches on the launching stream", "per_k": per_k}
 
     cpu = None

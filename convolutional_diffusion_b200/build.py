@@ -32,8 +32,10 @@ def build(force=False, verbose=False, profile=False):
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
+    extra = os.environ.get("CDS_EXTRA_NVCC_FLAGS", "").split()       # A/B builds: -D switches of the kernels
+    out = os.environ.get("CDS_BUILD_OUT", out)
     cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCDS_PROFILE_SWITCHES"] if profile else []) \
-        + ["-o", out] + srcs
+        + extra + ["-o", out] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -46,6 +46,17 @@
 #include <type_traits>
 #include "umma_common.cuh"
 
+// P.V epilogue: which column pairs of a 32-column unit form their weights with the FMA-pipe polynomial instead of MUFU.EX2.
+// Measured (profiles/r02q_*): per tile the epilogue costs a fixed ~750 cycles plus max(issue slots, MUFU cycles); with every
+// exponential on MUFU (16 lanes/clk/SM = 8 cycles per column) both are ~1900 cycles for 240 columns, so the polynomial only
+// pays together with the wide units that cut the instruction count.
+#ifndef CDS_PV_ABLATE
+#define CDS_PV_ABLATE 0            // A/B builds only (wrong results): see the uses
+#endif
+#ifndef CDS_PV_POLY_MASK
+#define CDS_PV_POLY_MASK 0x4444    // pairs 2, 6, 10, 14: a quarter of the exponentials
+#endif
+
 using namespace umma;
 
 namespace {
@@ -53,7 +64,9 @@ namespace {
 #ifdef CDS_PROFILE_SWITCHES
 // profile builds only: [0] warp-chunks seen, [1] warp-chunks skipped (all weights < 2^-40 of the running max),
 // [2] warp-chunks that raised a running max, [3] (warp, tile) units seen, [4] (warp, tile) units with every chunk skipped
-__device__ unsigned long long g_els_counters[8];
+// [8..10] MMA warp of the P.V variant, clock cycles summed over CTAs: waiting for barriers, issuing, tiles; [11..13] the same
+// for epilogue warp 0: waiting for the accumulators, working, tiles
+__device__ unsigned long long g_els_counters[16];
 #endif
 
 // ------------------------------------------------------------------ the kernel
@@ -62,6 +75,14 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const UmmaGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Warp roles.  The warp scheduler prefers the highest warp id among the eligible warps of a sub-partition, and the MMA warp
+  // must never wait for an issue slot (the tensor pipe queues only 2-3 UMMAs), so it takes the last warp; the epilogue
+  // warps come first (TMEM lane quadrant = warp % 4 either way).
+#ifndef CDS_ROLES_HEAD
+  constexpr int W_EPI0 = 0, W_PROD = 4 * NUM_EPI_WG, W_B0 = 4 * NUM_EPI_WG + 1, W_MMA = 4 * NUM_EPI_WG + 3;
+#else
+  constexpr int W_PROD = 0, W_MMA = 1, W_B0 = 2, W_EPI0 = 4;     // A/B: the round-1 assignment
+#endif
   const int tiles_j = (g.W + TJ - 1) / TJ;
   const int i0 = (blockIdx.x / tiles_j) * TI, j0 = (blockIdx.x % tiles_j) * TJ;
   const int split = blockIdx.y, b = blockIdx.z;
@@ -95,11 +116,11 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     for (int q = 0; q < 2; ++q) {
       mbar_init(bar_tfull + 8 * q, 1);
       mbar_init(bar_tempty + 8 * q, 4 * NUM_EPI_WG);      // every epilogue warp reads every tile (P.V: has stored its P)
-      mbar_init(bar_pvdone + 8 * q, 1);                   // P.V: commit after the P.V UMMAs of a tile
+      mbar_init(bar_pvdone + 8 * q, 1);                   // P.V: [0] = commit after the very last P.V
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
+  if (warp == W_B0) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
   // zero the staging area once: guard pads behind the tiles and band rows past the image bottom are never written by
   // the bulk copies, and whatever masked columns / zero-weighted K slots read there must stay finite
   for (int e = tid * 16; e < g.smem_stage; e += THREADS * 16) *reinterpret_cast<uint4*>(sStage + e) = make_uint4(0, 0, 0, 0);
@@ -181,7 +202,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   // ---- resident query slices: the first n_tmem K=16 slices of the A operand are copied into TMEM once (row q = lane q,
   // one column = two K elements), so those UMMAs stop re-reading 4 KB of shared memory per candidate tile
   if (PV) {          // O accumulator starts at zero: every P.V accumulates
-    if (warp >= 4 && warp < 8) {
+    if (warp >= W_EPI0 && warp < W_EPI0 + 4) {
       const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       tmem_st16(tmem_base + g.o_col + (((uint32_t)((warp & 3) * 32)) << 16), z);
       tmem_st_wait_all();
@@ -191,8 +212,8 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     tc_fence_after();
   }
   if (g.n_tmem > 0) {
-    if (warp >= 4 && warp < 8) {
-      const int q = tid - 128;
+    if (warp >= W_EPI0 && warp < W_EPI0 + 4) {
+      const int q = tid - 32 * W_EPI0;
       const uint32_t dst = tmem_base + g.a_tmem_col + (((uint32_t)((warp & 3) * 32)) << 16);
       for (int t = 0; t < g.n_tmem; ++t) {
         const uint32_t ex = p.table[t].x;
@@ -215,7 +236,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     }
   }
 
-  if (warp == 0) {
+  if (warp == W_PROD) {
     // =========================== producer: per (image, band) unit one bulk copy per channel (+ residual plane) of the
     // band's strip rows, and one of its norm-plane rows
     if (lane == 0) {
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // =========================== MMA issuer: the warp stays converged, one elected lane issues.  The descriptor
     // table is read from the kernel parameters (constant bank) with warp-uniform indices, so descriptor arithmetic
     // runs on the uniform datapath.
@@ -256,55 +277,56 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       // Issue order: S(0), S(1), P.V(0), S(2), P.V(1), ...  S(T+2) reuses the buffer of tile T and is issued after P.V(T),
       // which itself waits until every epilogue warp has read S(T) and stored P(T) over it; tensor-core operations
       // execute in issue order, so no barrier is needed between P.V(T) reading the buffer and S(T+2) overwriting it.
+      // The tensor pipe queues only two or three UMMAs ahead of the one it executes (measured: the issue of 10 UMMAs
+      // takes as long as their execution), so whatever this warp does between tiles is a bubble: one elected block per
+      // tile, descriptors from constant-bank tables, no divisions, no commit per P.V.
       const int nvb = g.nvb, nck = g.G >> 1;              // 16-column chunks per tile (every band has N = 8*G columns)
       const uint32_t idesc = (1u << 4) | (((uint32_t)(8 * g.G) >> 3) << 17) | ((128u >> 4) << 24);
       // P.V instruction: D = f32, A = B = f16, K-major, N = 16, M = 128, K = 16
       const uint32_t idesc_pv = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
       const int units = n_img * g.nchunks, total_tiles = units * nvb;
-      auto issue_pv = [&](int Tp) {
-        const int un = Tp / nvb, vb = Tp - un * nvb;
-        const int s = un & 1, buf = Tp & 1;
-        if (vb == 0) mbar_wait(bar_vready + 8 * s, (un >> 1) & 1, 7);          // V' operands of this band are built
-        mbar_wait(bar_pready + 8 * buf, (uint32_t)((Tp >> 1) & 1), 8);
+      const uint32_t o_col = tmem_base + g.o_col;
+      const uint32_t vring = smem_u32(sStage + g.v_ring_off) >> 4, vslot = (uint32_t)g.v_slot_bytes >> 4, vtile = (uint32_t)g.v_tile_bytes >> 4;
+      const uint32_t stage0 = smem_u32(sStage) >> 4, stage_sz = (uint32_t)g.stage_bytes >> 4;
+      int un = 0, vb = 0;                                 // band / tile-in-band of S(T)
+      int un2 = 0, vb2 = 0;                               // the same for P.V(T-2)
+#ifdef CDS_PROFILE_SWITCHES
+      long long ck_wait = 0, ck_issue = 0;
+#endif
+      for (int T = 0; T < total_tiles + 2; ++T) {
+        const bool do_pv = T >= 2, do_s = T < total_tiles;
+        const int s = un & 1, s2 = un2 & 1;
+        const uint32_t buf = (uint32_t)T & 1u;
+#ifdef CDS_PROFILE_SWITCHES
+        const long long ck0 = clock64();
+#endif
+        if (do_pv) {
+          if (vb2 == 0) mbar_wait(bar_vready + 8 * s2, (un2 >> 1) & 1, 7);          // V' operands of that band are built
+          mbar_wait(bar_pready + 8 * buf, (uint32_t)(((T - 2) >> 1) & 1), 8);       // P(T-2) is stored
+        }
+        if (do_s && vb == 0) mbar_wait(bar_full + 8 * s, (un >> 1) & 1, 2);
+#ifdef CDS_PROFILE_SWITCHES
+        const long long ck1 = clock64();
+        ck_wait += ck1 - ck0;
+#endif
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t st = smem_u32(sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes);
-          const uint32_t vbase = (st + g.v_data_off + (uint32_t)vb * g.v_tile_bytes) >> 4;
-          const uint32_t zpre = st >> 4, zpost = (st + g.v_zpost_off) >> 4;
-          const uint32_t s_col = tmem_base + buf * g.tmem_buf1, o_col = tmem_base + g.o_col;
-          const int rot = (Tp * nck) & 3;
+          const uint32_t d_tmem = tmem_base + buf * g.tmem_buf1;                     // S(T) and P(T-2) share the buffer
 #ifdef CDS_PROFILE_SWITCHES
-          if (!(p.flags & 16))          // profiling: 16 = no P.V UMMAs
+          if (do_pv && !(p.flags & 16)) {   // profiling: 16 = no P.V UMMAs
+#else
+          if (do_pv) {
 #endif
-          for (int j = 0; j < nck; ++j) {
-            // chunk j = patch rows 2j, 2j+1 of the band = two 128-byte core matrices (8 V' rows x 8 candidates).  Its owner
-            // warpgroup w accumulates in O columns 4w..4w+3: for w < 2 the value rows are the first 8-row group of the
-            // operand and the second group is the zero block behind the data; for w >= 2 the first group is the zero block
-            // in front of the data and the value rows are the second group (SBO = distance between the groups).
-            const int w = (j + rot) & 3;
-            const uint32_t vj = vbase + 16u * j;
-            const uint32_t start = w < 2 ? vj : zpre, sbo = w < 2 ? zpost - vj : vj - zpre;
-            const uint64_t bd = (1ull << 46) | ((uint64_t)(sbo & 0x3FFFu) << 32) | (8ull << 16) | (uint64_t)(start & 0x3FFFu);
-            umma_f16_ts(o_col, s_col + 16 * j, bd, idesc_pv, 1u);
+            const uint32_t vt = vring + s2 * vslot + vb2 * vtile;
+#pragma unroll 4
+            for (int j = 0; j < nck; ++j) {
+              const uint2 e = p.pv_table[j];
+              umma_f16_ts(o_col, d_tmem + 16 * j, ((uint64_t)e.y << 32) | (uint64_t)(e.x + vt), idesc_pv, 1u);
+            }
           }
-          umma_commit(bar_pvdone + 8 * buf);
-          if (vb == nvb - 1) umma_commit(bar_vempty + 8 * s);                   // last reader of this V' slot
-        }
-        __syncwarp();
-      };
-      int T = 0;
-      for (int un = 0; un < units; ++un) {
-        const int s = un & 1;
-        const uint32_t stage_addr = smem_u32(sStage + (size_t)s * g.stage_bytes);
-        for (int vb = 0; vb < nvb; ++vb, ++T) {
-          if (T >= 2) issue_pv(T - 2);      // first: it may be the commit that releases the stage the next band waits for
-          if (vb == 0) {
-            mbar_wait(bar_full + 8 * s, (un >> 1) & 1, 2);
-            tc_fence_after();
-          }
-          const uint32_t d_tmem = tmem_base + (T & 1) * g.tmem_buf1;
-          const uint32_t b_base = (stage_addr + vb * 128u) >> 4;
-          if (elect_one()) {
+          if (do_pv && vb2 == nvb - 1) umma_commit(bar_vempty + 8 * s2);            // last reader of that V' slot
+          if (do_s) {
+            const uint32_t b_base = stage0 + s * stage_sz + vb * 8u;
             int t = 0;
 #ifdef CDS_PROFILE_SWITCHES
             if (p.flags & 8) t = nm;      // profiling: 8 = no main UMMAs (accumulators keep whatever they held)
@@ -317,16 +339,28 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
               const uint2 e = p.table[t];
               umma_f16(d_tmem, a_hi | (uint64_t)(e.x + a_base), b_hi | (uint64_t)(e.y + b_base), idesc, t ? 1u : 0u);
             }
-            umma_commit(bar_tfull + 8 * (T & 1));
+            umma_commit(bar_tfull + 8 * buf);
             if (vb == nvb - 1) umma_commit(bar_empty + 8 * s);     // the stage's last main UMMAs: back to the producer
+          } else if (T == total_tiles + 1) {
+            umma_commit(bar_pvdone);      // after the very last P.V: the final drain of the epilogue waits for this
           }
-          __syncwarp();
         }
+        __syncwarp();
+#ifdef CDS_PROFILE_SWITCHES
+        ck_issue += clock64() - ck1;
+#endif
+        if (do_s && ++vb == nvb) { vb = 0; ++un; }
+        if (do_pv && ++vb2 == nvb) { vb2 = 0; ++un2; }
       }
-      if (total_tiles >= 2) issue_pv(total_tiles - 2);
-      issue_pv(total_tiles - 1);
+#ifdef CDS_PROFILE_SWITCHES
+      if (lane == 0) {
+        atomicAdd(&g_els_counters[8], (unsigned long long)ck_wait);
+        atomicAdd(&g_els_counters[9], (unsigned long long)ck_issue);
+        atomicAdd(&g_els_counters[10], (unsigned long long)total_tiles);
+      }
+#endif
       // nothing may still be executing on the tensor pipe when the CTA gives its TMEM back
-      mbar_wait(bar_pvdone + 8 * ((total_tiles - 1) & 1), (uint32_t)(((total_tiles - 1) >> 1) & 1), 10);
+      mbar_wait(bar_pvdone, 0u, 10);
     } else {
     long long T = 0;
     int unit = 0;
@@ -372,54 +406,56 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       }
     }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == W_B0 || warp == W_B0 + 1) {
     // =========================== builders: centre pixels of every candidate of the staged image, in tile order:
     // tile (ch,vb), column r = 8*gr + rr <-> patch (u0+gr, 8*vb+rr); pairs of columns are stored side by side
-    const int bt = tid - 64;   // 0..63
+    const int bt = tid - 32 * W_B0;   // 0..63
     int unit = 0;
     if constexpr (PV) {
-      // V' operand of the P.V contraction: per tile and patch row (= 8 candidates) one 128-byte core matrix of 8 rows x 8
-      // fp16: rows 4*(w&1) + c = scale * centre pixel of channel c (the bank's own fp16 values), row 4*(w&1) + 3 = 1 (softmax
-      // denominator), everything else 0, where w is the warpgroup that owns the chunk; candidates that are not valid
-      // patches get all-zero columns, which is what masks them in the sums
-      const int nck = g.G >> 1;
+      // V' operand of the P.V contraction: per tile and patch row kg (= 8 candidates) one 128-byte core matrix of 8 rows x 8
+      // fp16.  Chunk j = patch rows 2j, 2j+1 belongs to warpgroup w = (j >> 1) & 3; rows 4*(w&1) + c of its blocks = scale * centre
+      // pixel of channel c (the bank's own fp16 values), row 4*(w&1) + 3 = 1 for valid candidates (softmax denominator), everything
+      // else stays 0 from the initial clear.  One 16-byte load of strip granule (c, band row 8*b8 + d, x) yields the centre
+      // pixels of the eight patch rows kg = 8*b8 .. 8*b8+7 at image column x, i.e. of candidate rr = (x-d) & 7 of tile (x-d) >> 3.
+      const int nb8 = (g.G + 7) >> 3;
       for (int n = 0; n < n_img; ++n) {
         for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
           const int s = unit & 1, u0 = g.chunk_u0[ch];
           mbar_wait(bar_vempty + 8 * s, ((unit >> 1) & 1) ^ 1, 11);      // the band two before this one is done with the slot
           mbar_wait(bar_full + 8 * s, (unit >> 1) & 1, 6);
           const uint8_t* st = sStage + (size_t)s * g.stage_bytes;
-          uint8_t* vd = sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes + g.v_data_off;
-          for (int item = bt; item < g.nvb * g.G; item += 64) {
-            const int vb = item / g.G, kg = item - vb * g.G;
-            const int T = unit * g.nvb + vb;
-            const int hs = ((kg >> 1) + T * nck) & 1;                 // owner & 1: which half of the 8 rows carries values
-            const int u = u0 + kg;
-            uint32_t rows[4][4];                                       // [channel / ones][4 x f16x2]
+          uint8_t* vd = sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes + 256;    // operand blocks of tile 0
+          const int nrow = min(g.G, g.Ph - u0);                           // valid patch rows of this band
+#ifdef CDS_PROFILE_SWITCHES
+          if (!(p.flags & 256))       // profiling: 256 = the builders build nothing
+#endif
+          for (int item = bt; item < C * nb8 * g.Pw; item += 64) {
+            const int v = item % g.Pw, cb = item / g.Pw, b8 = cb % nb8, c = cb / nb8;
+            const uint4 gr = *reinterpret_cast<const uint4*>(st + ((size_t)(c * g.R + 8 * b8 + g.d) * g.W + (v + g.d)) * 16);
+            const uint32_t w4[4] = {gr.x, gr.y, gr.z, gr.w};
+            uint8_t* dst = vd + (size_t)(v >> 3) * g.v_tile_bytes + (size_t)(v & 7) * 2 + (size_t)c * 16;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-              for (int q = 0; q < 4; ++q) rows[c][q] = 0u;
-            if (u < g.Ph) {
-#pragma unroll
-              for (int rr = 0; rr < 8; ++rr) {
-                const int v = 8 * vb + rr;
-                if (v < g.Pw) {
-#pragma unroll
-                  for (int c = 0; c < C; ++c) {
-                    const size_t go = ((size_t)(c * g.R + kg + g.d) * g.W + (v + g.d)) * 16;   // band-relative row
-                    const uint32_t h = *reinterpret_cast<const uint16_t*>(st + go);
-                    rows[c][rr >> 1] |= h << (16 * (rr & 1));
-                  }
-                  rows[3][rr >> 1] |= 0x3C00u << (16 * (rr & 1));      // 1.0 in fp16
-                }
-              }
+            for (int e = 0; e < 8; ++e) {
+              const int kg = 8 * b8 + e;
+              if (kg < nrow)
+                *reinterpret_cast<uint16_t*>(dst + (size_t)kg * 128 + (size_t)(4 * ((kg >> 2) & 1)) * 16) =
+                    (uint16_t)(w4[e >> 1] >> (16 * (e & 1)));
             }
-            uint4* dst = reinterpret_cast<uint4*>(vd + (size_t)vb * g.v_tile_bytes + (size_t)kg * 128);
+          }
+          for (int item = bt; item < g.nvb * g.G; item += 64) {           // ones rows (validity can differ between bands)
+            const int vb = item / g.G, kg = item - vb * g.G;
+            uint32_t o4[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              dst[4 * hs + c] = make_uint4(rows[c][0], rows[c][1], rows[c][2], rows[c][3]);
-              dst[4 * (hs ^ 1) + c] = make_uint4(0, 0, 0, 0);
+            for (int q = 0; q < 4; ++q)
+              o4[q] = (kg < nrow && 8 * vb + 2 * q < g.Pw ? 0x3C00u : 0u) | (kg < nrow && 8 * vb + 2 * q + 1 < g.Pw ? 0x3C000000u : 0u);
+            *reinterpret_cast<uint4*>(vd + (size_t)vb * g.v_tile_bytes + (size_t)kg * 128 + (size_t)(4 * ((kg >> 2) & 1) + 3) * 16) =
+                make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          }
+          if (nrow < g.G) {     // a partial last band: rows that were valid in the previous band of this slot must read as zero
+            for (int item = bt; item < g.nvb * (g.G - nrow) * 4; item += 64) {
+              const int c = item & 3, rest = item >> 2, vb = rest / (g.G - nrow), kg = nrow + rest % (g.G - nrow);
+              *reinterpret_cast<uint4*>(vd + (size_t)vb * g.v_tile_bytes + (size_t)kg * 128 + (size_t)(4 * ((kg >> 2) & 1) + c) * 16) =
+                  make_uint4(0, 0, 0, 0);
             }
           }
           fence_proxy_async();           // generic-proxy writes above are read by the tensor core (async proxy)
@@ -470,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
     // its warp's 32 lanes) x FOUR columns (the pairs 2*t4 and 8+2*t4), so one 16-byte load of centre pixels per channel
     // serves 16 (query, candidate) pairs: a quarter of the shared-memory traffic of the row-per-thread 32x32b shape, and
     // shared-memory bandwidth (these loads + the UMMA operand reads) is what bounds the kernel.
-    const int wg = (warp - 4) >> 2, lq = warp & 3;
+    const int wg = (warp - W_EPI0) >> 2, lq = warp & 3;
     const uint32_t lane_addr = ((uint32_t)(lq * 32)) << 16;
     const float c1 = CDS_LOG2E * a / beta * inv_scale;   // accumulator -> log2-unit logit
     const float2 c1c1 = make_float2(c1, c1);
@@ -492,12 +528,17 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       const int nvb = g.nvb, nck = g.G >> 1;
 #ifdef CDS_PROFILE_SWITCHES
       unsigned cnt_chunks = 0, cnt_skipped = 0, cnt_exact = 0, cnt_drain = 0;
+      long long ek_wait = 0, ek_work = 0, ph_ld = 0, ph_cls = 0, ph_w = 0, ph_st = 0, ph_tail = 0;
 #endif
-      // folds the O accumulator (reference m_ref) into st and clears it; every P.V issued so far must be complete, i.e.
-      // the commit after the P.V of tile Tcur-1 (all earlier ones complete before it: issue order)
+      // folds the O accumulator (reference m_ref) into st and clears it.  Every P.V issued so far must be complete.  There
+      // is no commit per P.V (the MMA warp's per-tile work is a bubble on the tensor pipe); it issues P.V(T-2), S(T),
+      // P.V(T-1), S(T+1) in this order and commits tfull after every S, so the accumulators of tile Tcur+1 being ready
+      // implies that P.V(Tcur-1) and everything before it is done.  S(Tcur+1) does not depend on the epilogue of tile Tcur,
+      // so waiting for it here cannot deadlock.  The last drain waits for the commit after the very last P.V instead.
+      const uint32_t total_tiles = (uint32_t)(n_img * g.nchunks * g.nvb);
       auto drain = [&](uint32_t Tcur) {
-        const uint32_t Tp = Tcur - 1u;
-        mbar_wait(bar_pvdone + 8 * (Tp & 1u), (Tp >> 1) & 1u, 9);
+        if (Tcur + 1u < total_tiles) mbar_wait(bar_tfull + 8 * ((Tcur + 1u) & 1u), ((Tcur + 1u) >> 1) & 1u, 9);
+        else mbar_wait(bar_pvdone, 0u, 9);
         tc_fence_after();
         uint32_t o[4];
         tmem_ld4(o_addr, o);
@@ -520,7 +561,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       int unit = 0;
       for (int n = 0; n < n_img; ++n) {
         const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
-        if (n > 0 && (n & (n - 1)) == 0) {                 // re-base the reference before image 1, 2, 4, 8, ...
+        if (n > 0 && (n & (n - 1)) == 0 && T + 1u < total_tiles) {      // re-base the reference before image 1, 2, 4, 8, ...
           if (o_dirty) {
             drain(T);
 #ifdef CDS_PROFILE_SWITCHES
@@ -535,7 +576,14 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
           const int s = unit & 1;
           for (int vb = 0; vb < nvb; ++vb, ++T) {
             const uint32_t buf = T & 1u;
+#ifdef CDS_PROFILE_SWITCHES
+            const long long ek0 = clock64();
+#endif
             mbar_wait(bar_tfull + 8 * buf, (T >> 1) & 1u, 5);
+#ifdef CDS_PROFILE_SWITCHES
+            const long long ek1 = clock64();
+            ek_wait += ek1 - ek0;
+#endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + buf * g.tmem_buf1 + lane_addr;
             // an 8-column block that runs past the end of the image row aliases the next row's granules; for the band's last
@@ -543,79 +591,147 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
             // (and with it the reference): mask them explicitly.  Images whose width is a multiple of 8 never get here.
             const bool edge = 8 * vb + 8 > g.W;
             const int nval_v = g.Pw - 8 * vb, nval_u = g.Ph - g.chunk_u0[ch];
+            // Work unit of a warp = 32 accumulator columns (two 16-column chunks = two P.V UMMAs) of its 32 rows; unit u belongs
+            // to warpgroup u & 3.  Wide units matter: the epilogue is bound by instruction issue and latency, not by MUFU
+            // (measured: moving exponentials to an FMA-pipe polynomial made it slower), and the per-unit overhead (tcgen05
+            // ld / st with their warp syncs, votes, branches) is the same for 16 and 32 columns.
+            // kind: 0 = every weight rounds to zero (store zeros), 1 = regular, 2 = exact path (overflow / no reference yet)
+            auto unit32 = [&](int u, auto wide_tag) {
+              constexpr int NC = decltype(wide_tag)::value;          // 32, or 16 for the odd last chunk of a tile
+              const int j0c = 2 * u;                                 // first 16-column chunk of the unit
+              uint32_t r[NC];
+#ifdef CDS_PROFILE_SWITCHES
+              const long long pk0 = clock64();
+#endif
+#if CDS_PV_ABLATE & 4            // A/B builds only: no tcgen05.ld (registers hold an arbitrary finite pattern)
+              if (true) {
+#pragma unroll
+                for (int e = 0; e < NC; ++e) r[e] = __float_as_uint(-1000.f * (float)((e * 7 + lane) & 15));
+              } else
+#endif
+              if constexpr (NC == 32) {
+                tmem_ld_32x32b_x32(taddr + 16 * j0c, r);
+                tmem_ld_wait32(r);
+              } else {
+                tmem_ld16(taddr + 16 * j0c, r);
+                tmem_ld_wait16(r);
+              }
+#ifdef CDS_PROFILE_SWITCHES
+              const long long pk1 = clock64();
+              ph_ld += pk1 - pk0;
+#endif
+              if (edge) {
+#pragma unroll
+                for (int e = 0; e < NC; ++e)
+                  if ((e & 7) >= nval_v || 2 * j0c + (e >> 3) >= nval_u) r[e] = 0xff800000u;
+              }
+              float mx = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+              float mx2 = max3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
+#pragma unroll
+              for (int e = 6; e + 3 < NC; e += 4) {
+                mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+                mx2 = max3(mx2, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+              }
+              mx = max3(mx, mx2, __uint_as_float(r[NC - 2]));
+              mx = fmaxf(mx, __uint_as_float(r[NC - 1]));
+              const float lg = fmaf(mx, c1, lw);           // best logit of the unit for this row (c1 > 0)
+              m_seen = fmaxf(m_seen, lg);
+              const float dd = lg - m_ref;
+              int kind = 1;
+              // every weight rounds to zero in fp16 (< 2^-33 of the reference, which never exceeds the best logit seen): up to
+              // 4.5e6 such candidates add < 6e-4 of one top candidate's weight
+              if (__all_sync(0xffffffffu, dd < -PV_SKIP)) kind = 0;
+              // some weight would overflow fp16 (or there is no reference yet)
+              else if (__any_sync(0xffffffffu, !(dd <= PV_EXCEED))) kind = 2;
+#ifdef CDS_PROFILE_SWITCHES
+              ++cnt_chunks;
+              if (p.flags & 64) kind = 2;                  // profiling: 64 = every unit exact
+#endif
+              uint32_t pk[NC / 2];
+#ifdef CDS_PROFILE_SWITCHES
+              const long long pk2 = clock64();
+              ph_cls += pk2 - pk1;
+#endif
+              if (kind == 1) {
+#pragma unroll
+                for (int e = 0; e < NC / 2; ++e) {
+                  const float2 ar = fma2(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), c1c1, off2);
+#if (CDS_PV_ABLATE & 3) == 1      // A/B builds only: 1 = no MUFU, 2 = no F2FP, 3 = neither
+                  pk[e] = pack_f16x2(ar.x * 1e-3f, ar.y * 1e-3f); continue;
+#elif (CDS_PV_ABLATE & 3) == 2
+                  pk[e] = __float_as_uint(ex2(ar.x)) ^ __float_as_uint(ex2(ar.y)); continue;
+#elif (CDS_PV_ABLATE & 3) == 3
+                  pk[e] = __float_as_uint(ar.x) ^ __float_as_uint(ar.y); continue;
+#endif
+                  if ((CDS_PV_POLY_MASK >> e) & 1) {
+                    const float2 w = exp2_poly2(ar);
+                    pk[e] = pack_f16x2(w.x, w.y);
+                  } else {
+                    pk[e] = pack_f16x2(ex2(ar.x), ex2(ar.y));
+                  }
+                }
+                o_dirty = true;
+              } else {
+                if (kind == 2) {
+                  // exact online softmax on the CUDA cores for the 32 rows x NC candidates of this warp, P = 0.  The V' blocks
+                  // supply centre pixels and validity.
+                  mbar_wait(bar_vready + 8 * s, (unit >> 1) & 1, 4);
+                  const uint8_t* vblk = sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes + 256 + (size_t)vb * g.v_tile_bytes +
+                                        (size_t)(2 * j0c) * 128 + (size_t)(4 * (wg & 1)) * 16;
+#pragma unroll
+                  for (int e = 0; e < NC; ++e) {
+                    const uint8_t* col = vblk + (e >> 3) * 128 + (e & 7) * 2;
+                    if (*reinterpret_cast<const uint16_t*>(col + 3 * 16) != 0) {          // valid candidate (ones row)
+                      float v[C];
+#pragma unroll
+                      for (int c = 0; c < C; ++c) v[c] = __half2float(*reinterpret_cast<const __half*>(col + c * 16)) * inv_scale;
+                      st.push(fmaf(__uint_as_float(r[e]), c1, lw), v);
+                    }
+                  }
+#ifdef CDS_PROFILE_SWITCHES
+                  ++cnt_exact;
+#endif
+                }
+#ifdef CDS_PROFILE_SWITCHES
+                else ++cnt_skipped;
+#endif
+#pragma unroll
+                for (int e = 0; e < NC / 2; ++e) pk[e] = 0u;
+              }
+              // P of chunk j sits in the first 8 columns of the chunk's 16
+#if CDS_PV_ABLATE & 8            // A/B builds only: no tcgen05.st
+              if (pk[0] != 0x12345u || pk[NC / 2 - 1] != 0x54321u) return;
+#endif
+#ifdef CDS_PROFILE_SWITCHES
+              asm volatile("" : "+r"(pk[0]), "+r"(pk[NC / 2 - 1]));
+              const long long pk3 = clock64();
+              ph_w += pk3 - pk2;
+#endif
+              tmem_st8(taddr + 16 * j0c, pk);
+              if constexpr (NC == 32) tmem_st8(taddr + 16 * (j0c + 1), pk + 8);
+#ifdef CDS_PROFILE_SWITCHES
+              ph_st += clock64() - pk3;
+#endif
+            };
 #ifdef CDS_PROFILE_SWITCHES
             if (!(p.flags & 2))           // profiling: 2 = the epilogue touches nothing (tensor pipe + barriers only)
 #endif
-            for (int j = (int)((wg - T * nck) & 3u); j < nck; j += 4) {      // chunks owned by this warpgroup: (j + T*nck) % 4 == wg
-              uint32_t r[16];
-              tmem_ld16(taddr + 16 * j, r);
-              tmem_ld_wait16(r);
-              if (edge) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                  if ((e & 7) >= nval_v || 2 * j + (e >> 3) >= nval_u) r[e] = 0xff800000u;
-              }
-              float mx = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
-#pragma unroll
-              for (int e = 3; e < 15; e += 2) mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-              mx = fmaxf(mx, __uint_as_float(r[15]));
-              const float lg = fmaf(mx, c1, lw);           // best logit of the chunk for this row (c1 > 0)
-              m_seen = fmaxf(m_seen, lg);
-              const float dd = lg - m_ref;
-              uint32_t pk[8];
-#ifdef CDS_PROFILE_SWITCHES
-              ++cnt_chunks;
-#endif
-              if (__all_sync(0xffffffffu, dd < -PV_SKIP)) {
-                // every weight of the chunk rounds to zero in fp16 (< 2^-33 of the reference, which never exceeds the best
-                // logit seen): up to 4.5e6 such candidates add < 6e-4 of one top candidate's weight
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pk[e] = 0u;
-#ifdef CDS_PROFILE_SWITCHES
-                ++cnt_skipped;
-#endif
-#ifdef CDS_PROFILE_SWITCHES
-              } else if ((p.flags & 64) || __any_sync(0xffffffffu, !(dd <= PV_EXCEED))) {     // 64: every chunk exact
-#else
-              } else if (__any_sync(0xffffffffu, !(dd <= PV_EXCEED))) {
-#endif
-                // some weight would overflow fp16 (or there is no reference yet): exact online softmax on the CUDA cores
-                // for the 32 rows x 16 candidates of this warp, P = 0.  The V' block supplies centre pixels and validity.
-                mbar_wait(bar_vready + 8 * s, (unit >> 1) & 1, 4);
-                const uint8_t* vblk = sStage + g.v_ring_off + (size_t)s * g.v_slot_bytes + g.v_data_off + (size_t)vb * g.v_tile_bytes +
-                                      (size_t)(2 * j) * 128 + (size_t)(4 * (wg & 1)) * 16;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const uint8_t* col = vblk + (e >> 3) * 128 + (e & 7) * 2;
-                  if (*reinterpret_cast<const uint16_t*>(col + 3 * 16) != 0) {          // valid candidate (ones row)
-                    float v[C];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) v[c] = __half2float(*reinterpret_cast<const __half*>(col + c * 16)) * inv_scale;
-                    st.push(fmaf(__uint_as_float(r[e]), c1, lw), v);
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pk[e] = 0u;
-#ifdef CDS_PROFILE_SWITCHES
-                ++cnt_exact;
-#endif
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float2 ar = fma2(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), c1c1, off2);
-#ifdef CDS_PROFILE_SWITCHES
-                  if (p.flags & 32) { pk[e] = pack_f16x2(ar.x * 1e-3f, ar.y * 1e-3f); continue; }   // profiling: 32 = no MUFU
-#endif
-                  pk[e] = pack_f16x2(ex2(ar.x), ex2(ar.y));
-                }
-                o_dirty = true;
-              }
-              tmem_st8(taddr + 16 * j, pk);
+            for (int u = wg; 2 * u < nck; u += 4) {
+              if (2 * u + 1 < nck) unit32(u, std::integral_constant<int, 32>{});
+              else unit32(u, std::integral_constant<int, 16>{});
             }
+#ifdef CDS_PROFILE_SWITCHES
+            const long long ek2 = clock64();
+#endif
             tmem_st_wait_all();
             tc_fence_before();
             __syncwarp();
             if (elect_one()) mbar_arrive(bar_pready + 8 * buf);
+#ifdef CDS_PROFILE_SWITCHES
+            const long long ek3 = clock64();
+            ek_work += ek3 - ek1;
+            ph_tail += ek3 - ek2;
+#endif
           }
         }
       }
@@ -630,6 +746,16 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
         atomicAdd(&g_els_counters[1], (unsigned long long)cnt_skipped);
         atomicAdd(&g_els_counters[5], (unsigned long long)cnt_exact);
         atomicAdd(&g_els_counters[6], (unsigned long long)cnt_drain);
+        if (warp == W_EPI0 + (int)(blockIdx.x & 15)) {           // one warp per CTA, a different one from CTA to CTA
+          atomicAdd(&g_els_counters[11], (unsigned long long)ek_wait);
+          atomicAdd(&g_els_counters[12], (unsigned long long)ek_work);
+          atomicAdd(&g_els_counters[13], (unsigned long long)T);
+          atomicAdd(&g_els_counters[14], (unsigned long long)ph_ld);
+          atomicAdd(&g_els_counters[15], (unsigned long long)ph_cls);
+          atomicAdd(&g_els_counters[2], (unsigned long long)ph_w);
+          atomicAdd(&g_els_counters[3], (unsigned long long)ph_st);
+          atomicAdd(&g_els_counters[4], (unsigned long long)ph_tail);
+        }
       }
 #endif
     } else {
@@ -884,7 +1010,7 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W_B0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -930,7 +1056,7 @@ __global__ void norm_plane_kernel(const float* __restrict__ images, long long N,
 extern "C" int cds_debug_els_counters(unsigned long long* out_host8) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out_host8, g_els_counters, sizeof(g_els_counters));
-  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_els_counters, z, sizeof(z));
   return e == cudaSuccess ? CDS_OK : CDS_ERR_CUDA;
 }
@@ -986,13 +1112,13 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
   const char* mx = getenv("CDS_ELS_MIXED");     // A/B switch: 0 = vertical granules only
   const bool try_mixed = bank_rows != nullptr && !(mx && atoi(mx) == 0);
   CDS_CHECK_ARG(variant >= CDS_ELS_AUTO && variant <= CDS_ELS_PV, "cds_els_partials_umma: unknown variant %d", variant);
-  // P.V epilogue: single-plane banks, no dot-product dump.  "auto" uses it where it was measured faster: up to k = 13 the
-  // kernel is bound by the epilogue (MUFU + issue slots); from k = 15 by the main contraction, where the extra N=16 UMMAs
-  // of the P.V contraction cost more than the FMA-pipe weighted sum they replace.
+  // P.V epilogue: single-plane banks, no dot-product dump.  "auto" uses it where it was measured faster (profiles/r02*):
+  // up to k = 9 the kernel is bound by the epilogue; from k = 11 by the main contraction, where the extra N=16 UMMAs of the
+  // P.V contraction (~29 cycles each) cost more than the FMA-pipe weighted sum they replace.
   bool pv = false;
   if (variant != CDS_ELS_FMA && dbg_dots == nullptr) {
     const char* pk = getenv("CDS_PV_MAX_K");    // A/B switch for the auto rule
-    const int pv_max_k = pk ? atoi(pk) : 13;
+    const int pv_max_k = pk ? atoi(pk) : 9;
     if (variant == CDS_ELS_PV || k <= pv_max_k) pv = pick_geom(C, H, W, k, passes, planes, 1, try_mixed, p);
   }
   if (variant == CDS_ELS_PV && !pv) {
@@ -1018,6 +1144,7 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
   p.scale = bank_scale;
   p.idx = idx; p.logw = logw;
   p.m = m; p.l = l; p.acc = acc; p.dbg = dbg_dots;
+  make_pv_table(p.g, p.pv_table);
   {
     const char* f = getenv("CDS_DEBUG_FLAGS");
     p.flags = f ? atoi(f) : 0;

@@ -46,13 +46,11 @@ struct UmmaGeom {
   int o_col;          // P.V: TMEM column of the O accumulator (16 columns: 4 per epilogue warpgroup = C sums + denominator)
   // P.V: the V' operand lives in its own two-slot ring behind the stages (slot = band & 1), so that a stage can go back
   // to the producer as soon as the main UMMAs of its band are done, while V' stays until the band's last P.V (one tile
-  // later).  Slot layout: 256 zero bytes, per tile and patch row one 128-byte core matrix (8 rows x 8 candidates fp16),
-  // 256 zero bytes.
+  // later).  Slot layout: per tile [256 zero bytes][per patch row one 128-byte core matrix: 8 rows x 8 candidates fp16], and
+  // 256 more zero bytes behind the last tile; the zero block of tile vb+1 is the trailing zero block of tile vb.
   int v_ring_off;     // offset of slot 0 from the first stage
   int v_slot_bytes;
-  int v_data_off;     // offset of the operand blocks inside a slot (= 256)
-  int v_tile_bytes;   // bytes of V' per tile = G * 128
-  int v_zpost_off;    // offset of the trailing zero block inside a slot
+  int v_tile_bytes;   // distance between tiles = 256 + G * 128; the operand blocks of a tile start 256 bytes into it
   int stage_bytes;
   int stages;
   int nchunks, chunk_u0[MAX_CHUNKS], chunk_g[MAX_CHUNKS];
@@ -89,6 +87,7 @@ struct UmmaParams {
   int flags;               // profiling switches, honoured only when built with -DCDS_PROFILE_SWITCHES (CDS_DEBUG_FLAGS):
                            // 1 = pass 1 only, 2 = UMMAs only (no epilogue math), 8 = epilogue only (no UMMAs issued)
   uint2 table[MAX_MMAS];   // lo words of the (A,B) descriptors relative to the A base / the tile origin in a stage
+  uint2 pv_table[16];      // P.V: per 16-column chunk the V' descriptor (lo, hi word) relative to the tile's origin in its slot
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -184,6 +183,26 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for a 32-register load: the second statement ties registers 16..31 to the wait (volatile statements keep their order)
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t* r) {
+  tmem_ld_wait16(r);
+  asm volatile(""
+               : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -242,6 +261,24 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x for two values on the FMA pipe (no MUFU): round-to-nearest split x = n + f with the 1.5*2^23 trick, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] (max relative error 7.6e-5, a third of the fp16 half-ulp of the weights it feeds),
+// exponent patched in with an integer add.  x is clamped at -30 (the result, < 2^-30 * scale, rounds to 0 in fp16 anyway);
+// the caller guarantees x < 100.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 m1 = make_float2(-1.f, -1.f);
+  x.x = fmaxf(x.x, -30.f);
+  x.y = fmaxf(x.y, -30.f);
+  const float2 t = add2(x, magic);
+  const float2 n = add2(t, nmagic);
+  const float2 f = fma2(n, m1, x);
+  float2 q = fma2(f, make_float2(0.05520550534129143f, 0.05520550534129143f), make_float2(0.24261397123336792f, 0.24261397123336792f));
+  q = fma2(q, f, make_float2(0.6932547688484192f, 0.6932547688484192f));
+  q = fma2(q, f, make_float2(0.9999276995658875f, 0.9999276995658875f));
+  return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23)));
 }
 // one lane of a converged warp (the warp stays converged around it, so descriptors live in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -335,7 +372,7 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
     const int band = C * R * g.S1;
     const int hband = g.rem ? C * (G + g.rem - 1) * g.S1 + g.tile_pad : 0;
     const int vt_tile = pv ? 0 : 8 * G / 2 * 6;            // floats per tile of the centre-pixel table (FMA epilogue)
-    const int vring = pv ? 2 * ((512 + g.nvb * G * 128 + 127) / 128 * 128) : 0;
+    const int vring = pv ? 2 * (g.nvb * (256 + G * 128) + 256) : 0;
     const int stage = (bank_planes * (band + g.tile_pad) + hband + G * g.S1 + g.tile_pad + g.nvb * vt_tile * 4 + 127) / 128 * 128;
     const int st = fixed + vring + 2 * stage <= 227 * 1024 ? 2 : (fixed + vring + stage <= 227 * 1024 ? 1 : 0);
     // prefer two stages, then the cheapest tiling: candidate columns per image incl. padded patch rows, plus a fixed
@@ -355,10 +392,8 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   g.np_off = g.hb_off + (g.rem ? C * g.Rh * g.S1 + g.tile_pad : 0);
   g.vt_off = g.np_off + g.np_bytes + g.tile_pad;
   g.vt_tile = pv ? 0 : 8 * g.G / 2 * 6;                     // floats per tile (see UmmaGeom::vt_tile)
-  g.v_tile_bytes = g.G * 128;
-  g.v_data_off = 256;
-  g.v_zpost_off = g.v_data_off + g.nvb * g.v_tile_bytes;
-  g.v_slot_bytes = pv ? (g.v_zpost_off + 256 + 127) / 128 * 128 : 0;
+  g.v_tile_bytes = 256 + g.G * 128;
+  g.v_slot_bytes = pv ? g.nvb * g.v_tile_bytes + 256 : 0;
   g.stage_bytes = (g.vt_off + g.nvb * g.vt_tile * 4 + 127) / 128 * 128;
   g.stages = bestStages;
 
@@ -403,9 +438,9 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   // TMEM: two accumulator buffers of 8*G columns; what is left holds query K slices, which the tensor core then reads
   // from TMEM instead of re-reading them from shared memory for every candidate tile
   g.tmem_buf1 = 8 * g.G;
-  g.o_col = 2 * g.tmem_buf1;
-  g.a_tmem_col = 2 * g.tmem_buf1 + (pv ? 16 : 0);
-  g.n_tmem = (TMEM_COLS - g.a_tmem_col) / 8;
+  g.o_col = TMEM_COLS - 16;                                  // P.V: the O accumulator takes the last 16 columns
+  g.a_tmem_col = 2 * g.tmem_buf1;
+  g.n_tmem = (TMEM_COLS - (pv ? 16 : 0) - g.a_tmem_col) / 8;
   if (g.n_tmem > nm) g.n_tmem = nm;
   if (g.n_tmem < g.n_h) return 0;                            // the horizontal slices have no shared-memory copy
   g.v_ring_off = g.stages * g.stage_bytes;
@@ -414,5 +449,21 @@ inline int make_geom(int C, int H, int W, int k, int passes, int bank_planes, Um
   return g.smem_total <= 227 * 1024;
 }
 
+
+// V' descriptors of the P.V contraction (K-major, no swizzle, LBO = 128 B between the two K granules): chunk j = patch rows
+// 2j, 2j+1 of the tile = two 128-byte core matrices at 256 + 256*j.  Its owner warpgroup w = (j >> 1) & 3 accumulates in O columns
+// 4w..4w+3: for w < 2 the value rows are the first 8-row group of the operand and the second group is the zero block behind
+// the tile; for w >= 2 the first group is the zero block in front of the tile and the value rows are the second group
+// (SBO = distance between the groups).
+inline void make_pv_table(const UmmaGeom& g, uint2* t) {
+  const int nck = g.G / 2;
+  for (int j = 0; j < 16; ++j) {
+    const int data = 256 + 256 * (j < nck ? j : 0), zpost = 256 + g.G * 128;
+    const int w = (j >> 1) & 3;              // the epilogue works in units of two chunks (32 columns); unit u belongs to warpgroup u & 3
+    const int start = w < 2 ? data : 0, sbo = w < 2 ? zpost - data : data;
+    t[j].x = (uint32_t)(start >> 4) | (8u << 16);
+    t[j].y = (uint32_t)(sbo >> 4) | (1u << 14);          // bit 46 of the descriptor: version 1
+  }
+}
 
 }  // namespace umma

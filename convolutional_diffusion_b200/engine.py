@@ -48,7 +48,7 @@ class ScoreEngine:
         self.use_tensor_cores = use_tensor_cores
         self.group = group                       # torch.distributed process group for bank sharding (or None)
         # epilogue of the ELS tensor-core kernel: "auto" (P.V contraction on the tensor cores where supported and measured
-        # faster, k <= 13), "fma" (weighted sum on the FMA pipe), "pv" (P.V wherever supported); CDS_ELS_VARIANT overrides
+        # faster: k <= 9 and a/beta <= 100), "fma" (weighted sum on the FMA pipe), "pv" (P.V wherever supported); CDS_ELS_VARIANT overrides
         self.els_variant = os.environ.get("CDS_ELS_VARIANT", "auto")
         if self.els_variant not in _lib.ELS_VARIANT:
             raise ValueError(f"CDS_ELS_VARIANT must be one of {sorted(_lib.ELS_VARIANT)}, got {self.els_variant!r}")
@@ -78,6 +78,10 @@ class ScoreEngine:
         a_over_b = (max(1.0 - beta_min, 0.0) ** 0.5) / max(beta_min, 1e-6)
         root_d = k * self.bank.C ** 0.5
         return 1 if a_over_b * root_d <= 20.0 * min(1.0, 30.0 / root_d) else 2
+
+    @staticmethod
+    def _a_over_beta(beta_min):
+        return (max(1.0 - beta_min, 0.0) ** 0.5) / max(beta_min, 1e-6)
 
     def umma_supported(self, k, passes):
         b = self.bank
@@ -180,7 +184,7 @@ class ScoreEngine:
         self.launches += 1
         return P
 
-    def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma"):
+    def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma", a_over_beta=None):
         idx, logw, n_sel = sel
         if n_sel == 0:
             return self._empty_shard(tag, x.shape[0])
@@ -195,6 +199,10 @@ class ScoreEngine:
         variant = _lib.ELS_VARIANT[self.els_variant]
         if variant == 2 and (dbg is not None or not self.lib.cds_els_umma_pv_supported(b.C, b.H, b.W, k, passes, planes)):
             variant = 1                                            # "pv" means: wherever the geometry allows it
+        if variant == 0 and a_over_beta is not None and a_over_beta > 100.0:
+            # at the lowest noise levels most 16-column chunks carry no weight at all (77 % at a/beta = 165 on the headline
+            # trajectory): the FMA-pipe epilogue skips them outright, the P.V epilogue still stores and contracts zeros
+            variant = 1
         rows = b.rows8() if (k > 8 and k % 8) else None            # mixed K layout for the trailing k % 8 patch rows
         _lib.check(self.lib.cds_els_partials_umma(
             _lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(rows),
@@ -265,7 +273,7 @@ class ScoreEngine:
             pad = query_pad or "circular"
             passes = self.passes_for(k, beta_min)
             if self.umma_supported(k, passes):
-                P = self.umma_partials(pad, x, beta, k, sel, passes)
+                P = self.umma_partials(pad, x, beta, k, sel, passes, a_over_beta=self._a_over_beta(beta_min))
             else:
                 P = self.simt_partials("ELS", pad, x, beta, k, sel)
             self.finalize(self.combine(P), x, beta, mu, score)
@@ -273,7 +281,7 @@ class ScoreEngine:
             passes = self.passes_for(k, beta_min)
             d = k // 2
             if self.umma_supported(k, passes):
-                Pc = self.combine(self.umma_partials("zeros", x, beta, k, sel, passes))
+                Pc = self.combine(self.umma_partials("zeros", x, beta, k, sel, passes, a_over_beta=self._a_over_beta(beta_min)))
                 self.finalize(Pc, x, beta, mu, score, region=1, d=d)
                 if self.edge_supported(k) and self.ls_supported(k):
                     # edge bands: dedicated kernel; corners see only their own location = the LS kernel

@@ -103,7 +103,7 @@ int cds_bbels_edge_partials(const float* x, int B, int C, int H, int W, int k, c
  *   CDS_ELS_FMA  weights and weighted sums on the FMA pipe (any bank);
  *   CDS_ELS_PV   single sweep, the weights go back to TMEM as an fp16 operand and the weighted sum is a second
  *                contraction O += P.V' on the tensor cores (single-plane banks; error if the geometry is unsupported);
- *   CDS_ELS_AUTO P.V where it is supported and was measured faster (k <= 13), else FMA. */
+ *   CDS_ELS_AUTO P.V where it is supported and was measured faster (k <= 9), else FMA. */
 #define CDS_ELS_AUTO 0
 #define CDS_ELS_FMA  1
 #define CDS_ELS_PV   2

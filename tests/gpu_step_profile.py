@@ -52,16 +52,16 @@ def main():
         beta = torch.full((B,), beta_val, device="cuda")
         passes = eng.passes_for(k, beta_val)
         for _ in range(2):
-            eng.umma_partials("circular", x, beta, k, sel, passes)
+            eng.umma_partials("circular", x, beta, k, sel, passes, a_over_beta=eng._a_over_beta(beta_val))
         torch.cuda.synchronize()
-        cnt = (ctypes.c_ulonglong * 8)()
+        cnt = (ctypes.c_ulonglong * 16)()
         if have_counters:
             lib.cds_debug_els_counters(cnt)       # clear
         reps = 3
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
-            eng.umma_partials("circular", x, beta, k, sel, passes)
+            eng.umma_partials("circular", x, beta, k, sel, passes, a_over_beta=eng._a_over_beta(beta_val))
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
@@ -73,6 +73,9 @@ def main():
             c = [int(v) for v in cnt]
             extra = (f" {100.0 * c[1] / max(c[0], 1):.1f} {100.0 * c[4] / max(c[3], 1):.1f} {100.0 * c[2] / max(c[0], 1):.2f}"
                      f" exact%={100.0 * c[5] / max(c[0], 1):.3f} drains={c[6]}")
+            if c[10] and c[13]:
+                extra += (f" | clk/tile MMA wait={c[8] / c[10]:.0f} issue={c[9] / c[10]:.0f}  EPI wait={c[11] / c[13]:.0f} work={c[12] / c[13]:.0f}"
+                          f" [ld={c[14] / c[13]:.0f} max+classify={c[15] / c[13]:.0f} weights={c[2] / c[13]:.0f} st={c[3] / c[13]:.0f} tail={c[4] / c[13]:.0f}]")
         print(f"{r['i']:2d} {k:2d} {beta_val:.5f} {((1 - beta_val) ** 0.5) / beta_val:7.2f} {passes} {ms:7.3f} "
               f"{pairs / ms * 1e3:.3e} {pairs * 2 * k * k * 3 / ms * 1e-9:7.1f}{extra}")
     print(f"# sum of the 19 evaluations: {tot:.2f} ms")

@@ -21,17 +21,6 @@ using namespace umma;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 struct Res { unsigned long long cycles; unsigned sink; };
 
@@ -115,13 +104,20 @@ __global__ void __launch_bounds__(512, 1) ldst_kernel(int iters, Res* out) {
 // One elected lane issues `reps` groups of `per_group` UMMAs (M=128, N, K=16, f16) into alternating accumulators, one commit
 // per group, and waits for the last commit.  a_tmem: A operand from TMEM (columns 496..503) instead of shared memory.
 // small_every > 0: after every group, additionally issue `small_every` UMMAs with N=16 into columns 480..495 (the P.V pattern).
-__global__ void __launch_bounds__(128, 1) umma_kernel(int N, int per_group, int reps, int a_tmem, int small_every, Res* out) {
+// commits: tcgen05.commit instructions per group (onto scratch barriers nobody waits for; > 1 shows what a commit costs the pipe)
+__global__ void __launch_bounds__(128, 1) umma_kernel(int N, int per_group, int reps, int a_tmem, int small_every, Res* out,
+                                                      int commits = 0, int commit_split = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_scratch[4];
   const int warp = threadIdx.x >> 5;
   for (int e = threadIdx.x * 16; e < 64 * 1024; e += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + e) = make_uint4(0, 0, 0, 0);
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&s_bar[0]), 1); mbar_init(smem_u32(&s_bar[1]), 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1); mbar_init(smem_u32(&s_bar[1]), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_scratch[i]), 1 << 20);     // never completes: arrivals only
+    fence_barrier_init();
+  }
   if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
   fence_proxy_async();
   tc_fence_before();
@@ -151,7 +147,9 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(int N, int per_group, int 
         for (int i = 0; i < per_group; ++i) {
           if (a_tmem) umma_f16_ts(d, tbase + 496, bdesc, idesc, i ? 1u : 0u);
           else umma_f16(d, adesc, bdesc, idesc, i ? 1u : 0u);
+          if (commit_split && i == per_group / 2) umma_commit(smem_u32(&s_scratch[3]));   // a commit in the middle of a tile
         }
+        for (int i = 0; i < commits; ++i) umma_commit(smem_u32(&s_scratch[i & 3]));
         for (int i = 0; i < small_every; ++i) umma_f16_ts(tbase + 480, tbase + 496, bdesc, idesc16, 1u);
         if (g == reps - 1) umma_commit(smem_u32(&s_bar[0]));
       }
@@ -225,6 +223,16 @@ int main() {
     const unsigned long long cyc = run_max(d_out, sms);
     printf("umma  N=%3d per_group=%2d a_tmem=%d small=%2d  total=%llu  per_group=%.1f  per_main_umma=%.1f  (floor 128*N/256 = %.0f)\n",
            c.N, c.per, c.at, c.small, cyc, (double)cyc / reps, (double)cyc / reps / c.per, 128.0 * c.N / 256.0);
+  }
+  printf("# umma + commits: N=240, 10 per group, A from TMEM; commits per group / one more in the middle of the group\n");
+  for (int commits : {0, 1, 2, 3}) for (int split : {0, 1}) {
+    for (int rep = 0; rep < 2; ++rep) {
+      umma_kernel<<<sms, 128, 64 * 1024>>>(240, 10, reps, 1, 0, d_out, commits, split);
+      CK(cudaGetLastError());
+      CK(cudaDeviceSynchronize());
+    }
+    const unsigned long long cyc = run_max(d_out, sms);
+    printf("commit  commits=%d mid=%d  total=%llu  per_group=%.1f\n", commits, split, cyc, (double)cyc / reps);
   }
   CK(cudaFree(d_out));
   return 0;

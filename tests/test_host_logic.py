@@ -143,7 +143,7 @@ def test_umma_geometry_choices():
 def test_umma_pv_geometry_choices():
     """The same for the P.V epilogue (both query-pass counts): same bands and UMMA counts as the FMA epilogue, two stages
     (the stage of a band is released one tile late), the 16-column O accumulator fits next to the two S buffers; "auto"
-    takes P.V up to k = 13 and the FMA epilogue above."""
+    takes P.V up to k = 9 and the FMA epilogue above."""
     ks = (3, 5, 7, 9, 11, 13, 15, 17)
     for passes in (1, 2):
         geo = _umma_geometries(ks, variant=2, passes=passes)
@@ -155,7 +155,7 @@ def test_umma_pv_geometry_choices():
                 (ref[k]["G"], ref[k]["chunks"], ref[k]["nvb"], ref[k]["n_mma"], ref[k]["mixed"]), (k, passes, g, ref[k])
             assert 16 * g["G"] + 16 + 8 * g["n_tmem"] <= 512, (k, g)
     auto = _umma_geometries(ks, variant=0)
-    assert [auto[k]["pv"] for k in ks] == [1, 1, 1, 1, 1, 1, 0, 0]
+    assert [auto[k]["pv"] for k in ks] == [1, 1, 1, 1, 0, 0, 0, 0]
 
 
 def test_label_groups():
