@@ -41,6 +41,8 @@ SIGNATURES = {
     "cds_combine_packed": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "cds_finalize": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "cds_ddim_step": (_i, [_p, _p, _p, _p, _i, _i64, _p]),
+    "cds_finish": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "cds_randn_philox": (_i, [_p, _i64, _p, _i, _p]),
 }
 
 _lib = None

@@ -235,6 +235,102 @@ __global__ void finalize_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+// Philox4x32-10 (Salmon et al., SC'11; the generator behind cuRAND's and PyTorch's CUDA streams), written out so that the
+// stochastic sampler needs no library state and can live inside a captured CUDA graph
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// one standard normal per element: counter = (element index, stream offset + step), key = seed; Box-Muller on two words
+__device__ __forceinline__ float philox_normal(unsigned long long elem, unsigned long long seed, unsigned long long ctr) {
+  uint32_t w[4];
+  philox4x32_10((uint32_t)elem, (uint32_t)(elem >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed,
+                (uint32_t)(seed >> 32), w);
+  const float u1 = ((float)w[0] + 0.5f) * 2.3283064365386963e-10f;      // (0, 1]
+  const float u2 = ((float)w[1] + 0.5f) * 2.3283064365386963e-10f;
+  return sqrtf(-2.f * __logf(fminf(u1, 1.f))) * __cosf(6.283185307179586f * u2);
+}
+
+__global__ void randn_philox_kernel(float* __restrict__ out, long long n, const unsigned long long* __restrict__ so, int step) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g < n) out[g] = philox_normal((unsigned long long)g, so[0], so[1] + (unsigned long long)step);
+}
+
+// Fused tail of one evaluation: log-sum-exp merge of the S slices (same scheme as combine_kernel), mu, score, and the
+// sampler update in place.  stride_ml / stride_acc select the layout (separate arrays or all-gathered packed records).
+__global__ void finish_kernel(const float* __restrict__ m, const float* __restrict__ l, const float* __restrict__ acc, int S,
+                              int B, int C, int H, int W, size_t stride_ml, size_t stride_acc, int region, int d,
+                              float* __restrict__ x, const float* __restrict__ beta, float* __restrict__ mu,
+                              float* __restrict__ score, const float* __restrict__ cx, const float* __restrict__ cmu,
+                              const float* __restrict__ sigma, const float* __restrict__ noise,
+                              const unsigned long long* __restrict__ seed_offset, int step) {
+  __shared__ float sh[CMB_G][32][10];
+  const int HW = H * W;
+  const int lane = threadIdx.x, grp = threadIdx.y;
+  const int g = blockIdx.x * 32 + lane;
+  bool on = g < B * HW;
+  const int b = on ? g / HW : 0, pix = on ? g % HW : 0;
+  if (on && region != 0) {
+    const int i = pix / W, j = pix % W;
+    const bool rb = i < d || i >= H - d, cb = j < d || j >= W - d;
+    const bool centre = !rb && !cb, corner = rb && cb;
+    on = region == 1 ? centre : region == 2 ? !centre : region == 3 ? corner : (!centre && !corner);
+  }
+  float M = -INFINITY, L = 0.f, A[8];
+  for (int c = 0; c < C; ++c) A[c] = 0.f;
+  if (on) {
+    for (int s = grp; s < S; s += CMB_G) {
+      const size_t o = (size_t)s * stride_ml + (size_t)b * HW + pix;
+      const float ms = m[o];
+      if (ms == -INFINITY) continue;
+      const float Mn = fmaxf(M, ms);
+      const float w0 = exp2f(M - Mn), w1 = exp2f(ms - Mn);
+      L = L * w0 + l[o] * w1;
+      for (int c = 0; c < C; ++c) A[c] = A[c] * w0 + acc[(size_t)s * stride_acc + ((size_t)b * C + c) * HW + pix] * w1;
+      M = Mn;
+    }
+  }
+  sh[grp][lane][0] = M;
+  sh[grp][lane][1] = L;
+  for (int c = 0; c < C; ++c) sh[grp][lane][2 + c] = A[c];
+  __syncthreads();
+  if (grp != 0 || !on) return;
+  float Mt = -INFINITY;
+  for (int q = 0; q < CMB_G; ++q) Mt = fmaxf(Mt, sh[q][lane][0]);
+  float Lt = 0.f, At[8];
+  for (int c = 0; c < C; ++c) At[c] = 0.f;
+  for (int q = 0; q < CMB_G; ++q) {
+    const float mq = sh[q][lane][0];
+    const float w = (mq == -INFINITY) ? 0.f : exp2f(mq - Mt);
+    Lt = fmaf(sh[q][lane][1], w, Lt);
+    for (int c = 0; c < C; ++c) At[c] = fmaf(sh[q][lane][2 + c], w, At[c]);
+  }
+  const float bt = beta[b], a = sqrtf(1.f - bt), inv = 1.f / Lt;
+  for (int c = 0; c < C; ++c) {
+    const size_t o = ((size_t)b * C + c) * HW + pix;
+    const float mv = At[c] * inv, xv = x[o];
+    if (mu) mu[o] = mv;
+    if (score) score[o] = -(xv - a * mv) / bt;
+    if (cx) {
+      float xn = cx[b] * xv + cmu[b] * mv;
+      if (sigma) {
+        const float z = noise ? noise[o] : philox_normal((unsigned long long)o, seed_offset[0], seed_offset[1] + (unsigned long long)step);
+        xn = fmaf(sigma[b], z, xn);
+      }
+      x[o] = xn;
+    }
+  }
+}
+
 __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ cx,
                                  const float* __restrict__ cmu, int B, long long chw) {
   const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -335,5 +431,41 @@ extern "C" int cds_ddim_step(float* x, const float* mu, const float* c_x, const 
   const long long total = (long long)B * chw;
   ddim_step_kernel<<<(int)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(x, mu, c_x, c_mu, B, chw);
   CDS_CHECK_LAUNCH("ddim_step_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_finish(const float* m, const float* l, const float* acc, int packed, int S, int B, int C, int H, int W,
+                          int region, int d, float* x, const float* beta, float* mu, float* score, const float* c_x,
+                          const float* c_mu, const float* sigma, const float* noise, const uint64_t* seed_offset,
+                          int step, void* stream) {
+  CDS_CHECK_ARG(S >= 1 && C >= 1 && C <= 8 && B >= 1, "cds_finish: bad S=%d C=%d B=%d", S, C, B);
+  CDS_CHECK_ARG((c_x == nullptr) == (c_mu == nullptr), "cds_finish: c_x and c_mu come together");
+  CDS_CHECK_ARG(sigma == nullptr || (c_x != nullptr && (noise != nullptr || seed_offset != nullptr)),
+                "cds_finish: the stochastic update needs c_x/c_mu and either noise or a seed");
+  const int HW = H * W;
+  const size_t slice = (size_t)B * (2 + C) * HW;
+  const float* mm = m;
+  const float* ll = l;
+  const float* aa = acc;
+  size_t s_ml = (size_t)B * HW, s_acc = (size_t)B * C * HW;
+  if (packed) {                       // m points at the first rank's record [m | l | acc]
+    ll = m + (size_t)B * HW;
+    aa = m + (size_t)2 * B * HW;
+    s_ml = s_acc = slice;
+  }
+  const int blocks = (B * HW + 31) / 32;
+  finish_kernel<<<blocks, dim3(32, CMB_G), 0, (cudaStream_t)stream>>>(mm, ll, aa, S, B, C, H, W, s_ml, s_acc, region, d, x, beta,
+                                                                      mu, score, c_x, c_mu, sigma, noise,
+                                                                      (const unsigned long long*)seed_offset, step);
+  CDS_CHECK_LAUNCH("finish_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_randn_philox(float* out, int64_t n, const uint64_t* seed_offset, int step, void* stream) {
+  CDS_CHECK_ARG(n >= 1 && seed_offset != nullptr, "cds_randn_philox: bad arguments");
+  const int threads = 256;
+  randn_philox_kernel<<<(int)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      out, (long long)n, (const unsigned long long*)seed_offset, step);
+  CDS_CHECK_LAUNCH("randn_philox_kernel");
   return CDS_OK;
 }

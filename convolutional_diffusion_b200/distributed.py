@@ -51,6 +51,27 @@ def allgather_combine(engine, P, local_S):
     return P
 
 
+def allgather_packed(engine, P, local_S):
+    """First half of allgather_combine for the fused tail (cds_finish): merges this rank's CTA slices into its packed
+    record and all-gathers the records; returns (gathered [world * B*(2+C)*HW], world).  The merge across ranks then happens
+    inside cds_finish, in rank order on every rank (x stays bit-identical across ranks)."""
+    group = engine.group
+    world = dist.get_world_size(group)
+    key = ("packed", P.B)
+    if key not in engine._buf:
+        n = P.B * (2 + P.C) * P.HW
+        engine._buf[key] = (torch.empty(n, dtype=torch.float32, device=P.m.device),
+                            torch.empty(world * n, dtype=torch.float32, device=P.m.device))
+    mine, gathered = engine._buf[key]
+    bhw = P.B * P.HW
+    _lib.check(engine.lib.cds_combine(_lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), local_S, P.B, P.C, P.HW,
+                                      _lib.ptr(mine), _lib.ptr(mine[bhw:]), _lib.ptr(mine[2 * bhw:]),
+                                      _lib.stream_ptr()), "cds_combine")
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    engine.launches += 1
+    return gathered, world
+
+
 def init_from_env():
     """One process per GPU (torchrun): returns (rank, world, local_rank) and initialises NCCL if world > 1."""
     import os

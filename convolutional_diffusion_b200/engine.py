@@ -223,6 +223,25 @@ class ScoreEngine:
             self.launches += 1
         return P
 
+    def finish(self, P, x, beta, mu, score, region=0, d=0, step=None):
+        """Fused tail of one evaluation (cds_finish): merge of the CTA slices (and, with a process group, of the all-gathered
+        per-rank records), mu / score, and -- when `step` is given -- the sampler update of x in place.  `step` is a dict
+        with device tensors cx, cmu [B] and optionally sigma [B] plus noise [B,C,H,W] or seed_offset (uint64 [2]) and the
+        int `index` of the step (Philox counter)."""
+        b = self.bank
+        st = step or {}
+        sigma, noise, so = st.get("sigma"), st.get("noise"), st.get("seed_offset")
+        args = (x.shape[0], b.C, b.H, b.W, region, d, _lib.ptr(x), _lib.ptr(beta), _lib.ptr(mu), _lib.ptr(score),
+                _lib.ptr(st.get("cx")), _lib.ptr(st.get("cmu")), _lib.ptr(sigma), _lib.ptr(noise), _lib.ptr(so),
+                int(st.get("index", 0)), _lib.stream_ptr())
+        if self.group is not None:
+            from .distributed import allgather_packed
+            gathered, world = allgather_packed(self, P, P.S)
+            _lib.check(self.lib.cds_finish(_lib.ptr(gathered), None, None, 1, world, *args), "cds_finish")
+        else:
+            _lib.check(self.lib.cds_finish(_lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), 0, P.S, *args), "cds_finish")
+        self.launches += 1
+
     def finalize(self, P, x, beta, mu, score, region=0, d=0):
         b = self.bank
         _lib.check(self.lib.cds_finalize(_lib.ptr(x), _lib.ptr(beta), _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc),
@@ -237,9 +256,9 @@ class ScoreEngine:
         self.launches += 1
 
     # ---- one score evaluation ------------------------------------------------------------------
-    def evaluate(self, kind, x, beta, k, sel, query_pad=None, mu=None, score=None, beta_min=None, sel_ls=None):
-        """x [B,C,H,W] fp32 on device, beta [B] fp32 on device.  Writes mu and/or score (allocated if None
-        and requested by passing an empty tensor); returns (mu, score)."""
+    def evaluate(self, kind, x, beta, k, sel, query_pad=None, mu=None, score=None, beta_min=None, sel_ls=None, step=None):
+        """x [B,C,H,W] fp32 on device, beta [B] fp32 on device.  Writes mu and/or score when given; with `step` (see
+        finish) x is advanced in place by the sampler update.  Returns (mu, score)."""
         b = self.bank
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         assert tuple(x.shape[1:]) == (b.C, b.H, b.W), f"x {tuple(x.shape)} does not match bank {(b.C, b.H, b.W)}"
@@ -247,9 +266,9 @@ class ScoreEngine:
             raise RuntimeError(f"x lives on {x.device} but the bank of this engine on {self.device}")
         # the raw launches below go to the CURRENT device's stream: make the engine's device current for their duration
         with torch.cuda.device(self.device):
-            return self._evaluate(kind, x, beta, k, sel, query_pad, mu, score, beta_min, sel_ls)
+            return self._evaluate(kind, x, beta, k, sel, query_pad, mu, score, beta_min, sel_ls, step)
 
-    def _evaluate(self, kind, x, beta, k, sel, query_pad, mu, score, beta_min, sel_ls):
+    def _evaluate(self, kind, x, beta, k, sel, query_pad, mu, score, beta_min, sel_ls, step):
         b = self.bank
         if kind == "IS":                          # whole-image window: the LS kernel with k = 2*max(H,W)-1; the
             kind, k = "LS", 2 * max(b.H, b.W) - 1  # reference IS ignores k altogether (idealscore.py:583, **kwargs)
@@ -266,7 +285,7 @@ class ScoreEngine:
                 P = self.ls_partials(x, beta, k, sel)
             else:
                 P = self.simt_partials("LS", "zeros", x, beta, k, sel)
-            self.finalize(self.combine(P), x, beta, mu, score)
+            self.finish(P, x, beta, mu, score, step=step)
         elif kind == "ELS":
             if k > b.H or k > b.W:
                 raise ValueError(f"ELS needs kernel size <= image size, got k={k} for {b.H}x{b.W}")
@@ -276,25 +295,28 @@ class ScoreEngine:
                 P = self.umma_partials(pad, x, beta, k, sel, passes, a_over_beta=self._a_over_beta(beta_min))
             else:
                 P = self.simt_partials("ELS", pad, x, beta, k, sel)
-            self.finalize(self.combine(P), x, beta, mu, score)
+            self.finish(P, x, beta, mu, score, step=step)
         elif kind == "bbELS":
             passes = self.passes_for(k, beta_min)
             d = k // 2
+            # every partials kernel reads x, so all of them run before the first finish (which may advance x in place);
+            # the regions are disjoint sets of pixels, each finish touches only its own
             if self.umma_supported(k, passes):
-                Pc = self.combine(self.umma_partials("zeros", x, beta, k, sel, passes, a_over_beta=self._a_over_beta(beta_min)))
-                self.finalize(Pc, x, beta, mu, score, region=1, d=d)
+                Pc = self.umma_partials("zeros", x, beta, k, sel, passes, a_over_beta=self._a_over_beta(beta_min))
                 if self.edge_supported(k) and self.ls_supported(k):
                     # edge bands: dedicated kernel; corners see only their own location = the LS kernel
-                    Pe = self.combine(self.edge_partials(x, beta, k, sel))
-                    self.finalize(Pe, x, beta, mu, score, region=4, d=d)
-                    Pk = self.combine(self.ls_partials(x, beta, k, sel, tag="corner"))
-                    self.finalize(Pk, x, beta, mu, score, region=3, d=d)
+                    Pe = self.edge_partials(x, beta, k, sel)
+                    Pk = self.ls_partials(x, beta, k, sel, tag="corner")
+                    self.finish(Pc, x, beta, mu, score, region=1, d=d, step=step)
+                    self.finish(Pe, x, beta, mu, score, region=4, d=d, step=step)
+                    self.finish(Pk, x, beta, mu, score, region=3, d=d, step=step)
                 else:
-                    Pb = self.combine(self.simt_partials("bbELS", "zeros", x, beta, k, sel, region=2, tag="border"))
-                    self.finalize(Pb, x, beta, mu, score, region=2, d=d)
+                    Pb = self.simt_partials("bbELS", "zeros", x, beta, k, sel, region=2, tag="border")
+                    self.finish(Pc, x, beta, mu, score, region=1, d=d, step=step)
+                    self.finish(Pb, x, beta, mu, score, region=2, d=d, step=step)
             else:
-                P = self.combine(self.simt_partials("bbELS", "zeros", x, beta, k, sel))
-                self.finalize(P, x, beta, mu, score)
+                P = self.simt_partials("bbELS", "zeros", x, beta, k, sel)
+                self.finish(P, x, beta, mu, score, step=step)
         else:
             raise ValueError(f"unknown score module kind {kind!r}")
         return mu, score

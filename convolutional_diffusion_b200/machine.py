@@ -30,6 +30,26 @@ def ddim_coefficients(nsteps, schedule=cosine_noise_schedule):
     return out
 
 
+def ddpm_coefficients(nsteps, schedule=cosine_noise_schedule, first_step=None):
+    """The stochastic (DDPM) branch of the reference sampler, `DDIM.sample(ddpm=True)` (src/models.py:48-64):
+        sigma = sqrt(b'/b) sqrt(1 - a/a'),   x <- sqrt(a') (x - sqrt(b) eps)/sqrt(a) + sqrt(1 - a' - sigma^2) eps + sigma z
+    written in terms of the denoised estimate mu = (x - sqrt(b) eps)/sqrt(a):
+        x <- c_x x + c_mu mu + sigma z,   c_x = sqrt(b' - sigma^2)/sqrt(b),   c_mu = sqrt(a') - c_x sqrt(a).
+    Per step i = first_step ... 1: (i, beta_t, c_x, c_mu, sigma).  first_step defaults to nsteps-1 (the loop of
+    ScheduledScoreMachine.forward, idealscore.py:88); DDIM.sample itself starts at i = nsteps."""
+    out = []
+    for i in range(nsteps - 1 if first_step is None else int(first_step), 0, -1):
+        t = torch.tensor([i / nsteps], dtype=torch.float32)
+        bt = float(schedule(t))
+        bp = max(float(schedule(t - 1 / nsteps)), 0.0)
+        at, ap = 1.0 - bt, 1.0 - bp
+        sigma = math.sqrt(bp / bt) * math.sqrt(max(1.0 - at / ap, 0.0))
+        ce = math.sqrt(max(bp - sigma * sigma, 0.0))
+        cx = ce / math.sqrt(bt)
+        out.append((i, bt, cx, math.sqrt(ap) - cx * math.sqrt(at), sigma))
+    return out
+
+
 class ScheduledScoreMachine(nn.Module):
     def __init__(self, backbone, in_channels=3, imsize=32, default_time_steps=20,
                  noise_schedule=cosine_noise_schedule, score_backbone=True, scales=None, use_cuda_graph=True,
@@ -49,24 +69,37 @@ class ScheduledScoreMachine(nn.Module):
         self.max_cached_graphs = 32          # (nsteps, B, label, scales) keys; oldest evicted beyond this
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, x, nsteps=None, label=None, device=None, visualize=False):
+    def forward(self, x, nsteps=None, label=None, device=None, visualize=False, ddpm=False, noise=None, seed=None,
+                first_step=None):
+        """Deterministic DDIM trajectory as in the reference; ddpm=True takes the stochastic branch of the reference's
+        sampler (`DDIM.sample(ddpm=True)`, src/models.py:48-64) instead.  Its Gaussian noise is drawn on the device by a
+        Philox4x32-10 stream keyed by `seed` (default: one draw from torch's global RNG), inside the captured CUDA graph;
+        `noise` (a sequence of [B,C,H,W] tensors, one per step) injects given noise instead -- that is how the parity tests
+        replay a reference run.  first_step (DDPM only) starts the loop at another step, e.g. nsteps as DDIM.sample does."""
         if device is None:
             device = torch.device("cuda")
         if nsteps is None:
             nsteps = self.default_time_steps if self.scales is None else len(self.scales)
         native = isinstance(self.backbone, _ScoreModuleBase) and self.score_backbone \
             and self.backbone.schedule is self.noise_schedule
+        if ddpm and not native:
+            raise NotImplementedError("the stochastic sampler runs on this package's score modules only")
+        sto = None
+        if ddpm:
+            sto = dict(noise=noise, seed=int(torch.empty((), dtype=torch.int64).random_().item()) if seed is None else int(seed),
+                       first_step=first_step)
         groups = _label_groups(label, x.shape[0]) if native else None
         if groups is not None:                   # per-sample labels: one trajectory per distinct label
             out = None
             for lab_g, rows in groups.items():
-                res = self._forward_native(x[rows], nsteps, lab_g, torch.device(device))
+                sub = None if sto is None else dict(sto, noise=None if noise is None else [z[rows] for z in noise])
+                res = self._forward_native(x[rows], nsteps, lab_g, torch.device(device), sto=sub)
                 if out is None:
                     out = torch.empty((x.shape[0],) + tuple(res.shape[1:]), dtype=res.dtype, device=res.device)
                 out[torch.as_tensor(rows, device=res.device)] = res
             return out
         if native:
-            return self._forward_native(x, nsteps, _as_label(label), torch.device(device))
+            return self._forward_native(x, nsteps, _as_label(label), torch.device(device), sto=sto)
         return self._forward_generic(x, nsteps, label, device)
 
     def sample(self, nsteps=None, label=None, device=None):
@@ -97,15 +130,22 @@ class ScheduledScoreMachine(nn.Module):
         return x
 
     # ---- native loop: device resident, graph captured ----------------------------------------------
-    def _plan(self, nsteps, B, device):
+    def _plan(self, nsteps, B, device, sto=None):
         mod = self.backbone
         steps = []
-        for i, bt, cx, cmu in ddim_coefficients(nsteps, self.noise_schedule):
-            k = mod.kernel_size if self.scales is None else int(self.scales[i])
-            steps.append(dict(i=i, k=k, beta=bt,
-                              beta_dev=torch.full((B,), bt, dtype=torch.float32, device=device),
-                              cx=torch.full((B,), cx, dtype=torch.float32, device=device),
-                              cmu=torch.full((B,), cmu, dtype=torch.float32, device=device)))
+        if sto is None:
+            coeffs = [(i, bt, cx, cmu, None) for i, bt, cx, cmu in ddim_coefficients(nsteps, self.noise_schedule)]
+        else:
+            coeffs = ddpm_coefficients(nsteps, self.noise_schedule, sto.get("first_step"))
+        for i, bt, cx, cmu, sigma in coeffs:
+            k = mod.kernel_size if self.scales is None else int(self.scales[min(i, len(self.scales) - 1)])
+            st = dict(i=i, k=k, beta=bt,
+                      beta_dev=torch.full((B,), bt, dtype=torch.float32, device=device),
+                      cx=torch.full((B,), cx, dtype=torch.float32, device=device),
+                      cmu=torch.full((B,), cmu, dtype=torch.float32, device=device), index=i)
+            if sigma is not None:
+                st["sigma"] = torch.full((B,), sigma, dtype=torch.float32, device=device)
+            steps.append(st)
         return steps
 
     def _run_steps(self, eng, steps, x, mu, sel, sel_ls, record=None, label=None, reselect=False):
@@ -123,13 +163,14 @@ class ScheduledScoreMachine(nn.Module):
                         sel = mod.selection(label)
                 else:
                     sel = mod.selection(label)
+            x_before = x.clone() if record is not None else None
+            # one fused tail per evaluation: merge of the partials, mu, and the sampler update of x in place
             eng.evaluate(mod.kind, x, st["beta_dev"], st["k"], sel, query_pad=mod.query_pad, mu=mu, score=None,
-                         beta_min=st["beta"], sel_ls=sel_ls)
+                         beta_min=st["beta"], sel_ls=sel_ls, step=st)
             if record is not None:
-                record.append(dict(i=st["i"], k=st["k"], beta=st["beta"], x=x.clone(), mu=mu.clone()))
-            eng.ddim_step(x, mu, st["cx"], st["cmu"])
+                record.append(dict(i=st["i"], k=st["k"], beta=st["beta"], x=x_before, mu=mu.clone()))
 
-    def _forward_native(self, x, nsteps, label, device, record=None):
+    def _forward_native(self, x, nsteps, label, device, record=None, sto=None):
         mod = self.backbone
         eng = mod.engine(device)
         B = x.shape[0]
@@ -145,16 +186,29 @@ class ScheduledScoreMachine(nn.Module):
         else:
             sel = mod.selection(label)
             sel_ls = mod.selection(label, kind="LS") if needs_ls else None
-        key = (nsteps, B, label, tuple(self.scales) if self.scales is not None else None)
+        injected = sto is not None and sto.get("noise") is not None
+        key = (nsteps, B, label, tuple(self.scales) if self.scales is not None else None,
+               None if sto is None else ("ddpm", sto.get("first_step")))
         with torch.cuda.device(eng.device):
-            if record is not None or not self.use_cuda_graph or shuffled:
+            if record is not None or not self.use_cuda_graph or shuffled or injected:
                 xw = x.to(eng.device, torch.float32).clone().contiguous()
                 mu = torch.empty_like(xw)
-                self._run_steps(eng, self._plan(nsteps, B, eng.device), xw, mu, sel, sel_ls, record, label=label,
-                                reselect=bool(shuffled))
+                steps = self._plan(nsteps, B, eng.device, sto)
+                if sto is not None:
+                    so = torch.tensor([sto["seed"], 0], dtype=torch.int64, device=eng.device)
+                    for q, st in enumerate(steps):
+                        st["seed_offset"] = so
+                        if injected:
+                            st["noise"] = sto["noise"][q].to(eng.device, torch.float32).contiguous()
+                self._run_steps(eng, steps, xw, mu, sel, sel_ls, record, label=label, reselect=bool(shuffled))
                 return xw
             if key not in self._graphs:
-                steps = self._plan(nsteps, B, eng.device)
+                steps = self._plan(nsteps, B, eng.device, sto)
+                so = None
+                if sto is not None:          # the seed lives in a device buffer: rewritten before every replay
+                    so = torch.zeros(2, dtype=torch.int64, device=eng.device)
+                    for st in steps:
+                        st["seed_offset"] = so
                 xs = torch.zeros(B, eng.bank.C, eng.bank.H, eng.bank.W, dtype=torch.float32, device=eng.device)
                 mu = torch.empty_like(xs)
                 eng.bank.strip8()
@@ -169,9 +223,11 @@ class ScheduledScoreMachine(nn.Module):
                     self._run_steps(eng, steps, xs, mu, sel, sel_ls)
                 while len(self._graphs) >= self.max_cached_graphs:
                     self._graphs.pop(next(iter(self._graphs)))
-                self._graphs[key] = (graph, xs, mu, steps, sel, sel_ls)
-            graph, xs, mu, *_ = self._graphs[key]
+                self._graphs[key] = (graph, xs, mu, steps, sel, sel_ls, so)
+            graph, xs, mu, _steps, _sel, _sel_ls, so = self._graphs[key]
             xs.copy_(x.to(eng.device, torch.float32))
+            if so is not None:
+                so.copy_(torch.tensor([sto["seed"], 0], dtype=torch.int64))
             graph.replay()
             return xs.clone()
 

@@ -128,7 +128,7 @@ class _ScoreModuleBase(nn.Module):
     def _ls_shuffles(self):
         """LS hard-codes shuffle=True (idealscore.py:489); the order only matters when batches end up with
         unequal post-filter sizes, so skip the permutation when a single batch covers the bank."""
-        return self.batch_size < len(self.dataset)
+        return self.batch_size < self.engine().bank.N          # not len(dataset): an (images, labels) pair has length 2
 
     def betas(self, t, device):
         return self.schedule(torch.as_tensor(t, dtype=torch.float32).reshape(-1).cpu()).to(device, torch.float32)

@@ -134,6 +134,23 @@ int cds_combine_packed(const float* packed, int S, int B, int C, int HW, float* 
 int cds_finalize(const float* x, const float* beta, const float* m, const float* l, const float* acc,
                  int B, int C, int H, int W, int region, int d, float* mu, float* score, void* stream);
 
+/* Fused tail of one score evaluation: the log-sum-exp merge of cds_combine (packed = 0: S slices in m / l / acc) or
+ * cds_combine_packed (packed = 1: m points at S all-gathered records [m | l | acc], l and acc are ignored), mu and score as
+ * cds_finalize (same region / d), and -- when c_x is given -- the sampler update in place
+ *     x <- c_x[b] x + c_mu[b] mu (+ sigma[b] z),   z ~ N(0,1)
+ * i.e. the DDIM step of ScheduledScoreMachine.forward (idealscore.py:101-116) or, with sigma, the DDPM branch of
+ * DDIM.sample (src/models.py:48-64) written in terms of the denoised estimate.  z is read from noise [B][C][H*W] when given,
+ * else drawn from Philox4x32-10: key = seed_offset[0], counter = (element index, seed_offset[1] + step); seed_offset is a
+ * DEVICE buffer of two uint64 so that a captured CUDA graph replays with fresh noise after the host rewrites it.
+ * One launch replaces combine -> finalize -> ddim_step (and combine_packed -> finalize -> ddim_step across ranks). */
+int cds_finish(const float* m, const float* l, const float* acc, int packed, int S, int B, int C, int H, int W,
+               int region, int d, float* x, const float* beta, float* mu, float* score, const float* c_x,
+               const float* c_mu, const float* sigma, const float* noise, const uint64_t* seed_offset, int step,
+               void* stream);
+
+/* out[i] = the standard normal cds_finish draws for element i at this (seed_offset, step); tests and seeding only */
+int cds_randn_philox(float* out, int64_t n, const uint64_t* seed_offset, int step, void* stream);
+
 /* one deterministic DDIM update of ScheduledScoreMachine.forward (idealscore.py:101-116) written in terms
  * of the denoised estimate:  x <- c_x[b]*x + c_mu[b]*mu  */
 int cds_ddim_step(float* x, const float* mu, const float* c_x, const float* c_mu, int B, int64_t chw,

@@ -113,6 +113,54 @@ def module_cases(ref):
     ]
     for kind, c, h, n, k, t, label, bs, ms, seed in more:
         cases.append(_one_module_case(ref, kind, c, h, n, k, t, label, bs, ms, seed))
+    # round 2 (appended): bbELS at the CIFAR shape for small and medium kernel sizes, and the kernel sizes of the UNet scales
+    # files (checkpoints/scales_*UNet*.pt reach 25 and 27) for ELS and bbELS
+    round2 = [
+        ("bbELS", 3, 32, 8, 3, 0.15, None, 8, None, 13),
+        ("bbELS", 3, 32, 8, 7, 0.40, 1, 4, None, 14),
+        ("bbELS", 3, 32, 8, 11, 0.65, None, 8, None, 15),
+        ("ELS", 3, 32, 6, 19, 0.92, None, 6, None, 16),
+        ("ELS", 3, 32, 6, 25, 0.95, None, 6, None, 17),
+        ("ELS", 1, 32, 8, 27, 0.95, None, 8, None, 18),
+        ("bbELS", 3, 32, 6, 19, 0.92, None, 6, None, 16),
+        ("bbELS", 3, 32, 6, 25, 0.95, None, 6, None, 17),
+        ("bbELS", 1, 32, 8, 27, 0.95, None, 8, None, 18),
+    ]
+    for kind, c, h, n, k, t, label, bs, ms, seed in round2:
+        cases.append(_one_module_case(ref, kind, c, h, n, k, t, label, bs, ms, seed))
+    return cases
+
+
+def machinex_cases(ref):
+    """Trajectories outside the plain (kind, scales) pattern: an IdealScoreModule backbone without a scales list
+    (ScheduledScoreMachine then runs default_time_steps steps and passes k=None, idealscore.py:85-95), and LS with
+    batch_size < N plus a label, where the reference opens a freshly shuffled DataLoader at every evaluation (two draws
+    from the global torch RNG each, idealscore.py:489,521) -- the test replays it from the same torch seed."""
+    cases = []
+    # IS, no scales
+    bank, labels = synthetic_bank(24, 3, 12, nlabels=3, seed=21)
+    mod = _module(ref, "IS", ref_loader.TensorBank(bank, labels), 3, 8, None)
+    machine = ref.ScheduledScoreMachine(mod, in_channels=3, imsize=12, default_time_steps=6, score_backbone=True)
+    x = torch.randn(1, 3, 12, 12, generator=torch.Generator().manual_seed(221))
+    with torch.no_grad():
+        out = machine(x.clone(), label=torch.tensor([1]), device=torch.device("cpu"))
+    cases.append(dict(kind="IS", bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(), scales=np.zeros(0, np.int64),
+                      nsteps=np.int64(6), label=np.int64(1), batch_size=np.int64(8), torch_seed=np.int64(-1),
+                      out=out.numpy()))
+    print(f"machinex IS no scales: |out|max={out.abs().max():.3f}")
+    # LS, shuffled batches of unequal post-filter size
+    bank, labels = synthetic_bank(40, 3, 12, nlabels=3, seed=22)
+    scales = [3, 3, 5, 5, 7, 7]
+    mod = _module(ref, "LS", ref_loader.TensorBank(bank, labels), 3, 16, None)
+    machine = ref.ScheduledScoreMachine(mod, in_channels=3, imsize=12, scales=scales, score_backbone=True)
+    x = torch.randn(1, 3, 12, 12, generator=torch.Generator().manual_seed(222))
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        out = machine(x.clone(), label=torch.tensor([2]), device=torch.device("cpu"))
+    cases.append(dict(kind="LS", bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(),
+                      scales=np.asarray(scales, dtype=np.int64), nsteps=np.int64(len(scales)), label=np.int64(2),
+                      batch_size=np.int64(16), torch_seed=np.int64(1234), out=out.numpy()))
+    print(f"machinex LS shuffled: |out|max={out.abs().max():.3f}")
     return cases
 
 
@@ -149,6 +197,35 @@ def machine_cases(ref):
     return cases
 
 
+def ddpm_cases(ref):
+    """The stochastic branch of the reference sampler, `DDIM.sample(ddpm=True)` (src/models.py:48-64), driven by the
+    reference's own analytic score module: the backbone handed to DDIM returns eps = -sqrt(beta) * score.  The Gaussian
+    noise comes from torch's global CPU generator (randn_like, one draw per step); the test regenerates the same draws
+    from `torch_seed` and injects them."""
+    models = ref_loader.load_models()
+    cases = []
+    for kind, c, h, n, k, nsteps, label, bs, seed in [("ELS", 3, 12, 32, 5, 8, None, 16, 31), ("bbELS", 1, 16, 24, 3, 6, 1, 8, 32)]:
+        bank, labels = synthetic_bank(n, c, h, nlabels=3, seed=seed)
+        mod = _module(ref, kind, ref_loader.TensorBank(bank, labels), k, bs, None)
+
+        class EpsBackbone(torch.nn.Module):
+            def forward(self, t, x, label=None):
+                s = mod(t.cpu(), x, label=label, device=torch.device("cpu"))
+                return -ref.cosine_noise_schedule(t.cpu())[:, None, None, None] ** 0.5 * s
+
+        sampler = models.DDIM(backbone=EpsBackbone(), in_channels=c, noise_schedule=ref.cosine_noise_schedule, default_imsize=h)
+        x = torch.randn(1, c, h, h, generator=torch.Generator().manual_seed(300 + seed))
+        lab = None if label is None else torch.tensor([label])
+        torch.manual_seed(4000 + seed)
+        with torch.no_grad():
+            out = sampler.sample(batch_size=1, x=x.clone(), nsteps=nsteps, label=lab, device=torch.device("cpu"), ddpm=True)
+        cases.append(dict(kind=kind, bank=bank.numpy(), labels=labels.numpy(), x=x.numpy(), nsteps=np.int64(nsteps),
+                          k=np.int64(k), label=np.int64(-1 if label is None else label), batch_size=np.int64(bs),
+                          torch_seed=np.int64(4000 + seed), out=out.numpy()))
+        print(f"ddpm {kind} C={c} H={h} N={n} k={k} nsteps={nsteps}: |out|max={out.abs().max():.3f}")
+    return cases
+
+
 def schedule_cases(ref):
     t = torch.arange(0, 21, dtype=torch.float32) / 20
     return dict(t=t.numpy(), cosine=ref.cosine_noise_schedule(t).numpy(),
@@ -179,6 +256,10 @@ def main():
         save(f"module_{i:02d}_{c['kind']}.npz", c)
     for i, c in enumerate(machine_cases(ref)):
         save(f"machine_{i:02d}_{c['kind']}.npz", c)
+    for i, c in enumerate(machinex_cases(ref)):
+        save(f"machinex_{i:02d}_{c['kind']}.npz", c)
+    for i, c in enumerate(ddpm_cases(ref)):
+        save(f"ddpm_{i:02d}_{c['kind']}.npz", c)
     save("schedule.npz", schedule_cases(ref))
     save("scales.npz", scales_files())
 

@@ -37,6 +37,13 @@ def load():
     return importlib.import_module("src.utils.idealscore")
 
 
+def load_models():
+    """Returns the reference's `src.models` (the DDIM wrapper whose sample() holds the DDPM branch, models.py:48-64)."""
+    load()
+    import importlib
+    return importlib.import_module("src.models")
+
+
 class TensorBank:
     """Minimal map-style dataset yielding (image [C,H,W] float32, int label), the protocol the
     reference's DataLoader consumes (idealscore.py:142,390,489)."""

@@ -302,6 +302,62 @@ def run_machine(kind, x, bank, scales, logw=None, nsteps=None, default_k=3, sche
     return x
 
 
+def ddpm_coeffs(nsteps, schedule=cosine_beta, first_step=None):
+    """Per-step (i, beta_t, c_mu, c_eps, sigma) of the stochastic branch of the reference sampler (src/models.py:48-64):
+        sigma = sqrt(b'/b) sqrt(1 - a/a'),  x <- sqrt(a') * (x - sqrt(b) eps)/sqrt(a) + sqrt(1 - a' - sigma^2) eps + sigma z
+    The loop of DDIM.sample starts at i = nsteps (first_step = None), ScheduledScoreMachine's at nsteps - 1."""
+    out = []
+    for i in range(nsteps if first_step is None else first_step, 0, -1):
+        bt = float(schedule(i / nsteps))
+        bp = max(float(schedule(i / nsteps - 1.0 / nsteps)), 0.0)
+        at, ap = 1.0 - bt, 1.0 - bp
+        sigma = math.sqrt(bp / bt) * math.sqrt(max(1.0 - at / ap, 0.0))
+        out.append((i, bt, math.sqrt(ap), math.sqrt(max(1.0 - ap - sigma * sigma, 0.0)), sigma))
+    return out
+
+
+def run_machine_ddpm(kind, x, bank, k, nsteps, noises, logw=None, schedule=cosine_beta, first_step=None, scales=None):
+    """DDIM.sample(ddpm=True) (src/models.py:48-64) for one sample with eps = -sqrt(beta) * score of the analytic module;
+    noises[q] [C,H,W] is the Gaussian draw of the q-th step."""
+    x = np.array(x, dtype=np.float64)
+    for q, (i, bt, c_mu, c_eps, sigma) in enumerate(ddpm_coeffs(nsteps, schedule, first_step)):
+        kk = k if scales is None else int(scales[min(i, len(scales) - 1)])
+        s, mu = score(kind, x, bank, bt, kk, logw)
+        eps = -math.sqrt(bt) * s
+        x = c_mu * (x - math.sqrt(bt) * eps) / math.sqrt(1.0 - bt) + c_eps * eps + sigma * np.asarray(noises[q], dtype=np.float64)
+    return x
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11) on uint32 numpy arrays: counter [..., 4], key [..., 2] -> [..., 4].  Restates the
+    generator of csrc/simt_kernels.cu so that the device noise stream of the stochastic sampler can be checked bit for bit."""
+    c = [np.asarray(counter[..., j], dtype=np.uint64) for j in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint64)
+    k1 = np.asarray(key[..., 1], dtype=np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        n0 = ((p1 >> np.uint64(32)) ^ c[1] ^ k0) & m32
+        n2 = ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & m32
+        c = [n0, p1 & m32, n2, p0 & m32]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_normal(n, seed, ctr):
+    """The n standard normals cds_randn_philox / cds_finish draw for elements 0..n-1 at stream position ctr."""
+    e = np.arange(n, dtype=np.uint64)
+    counter = np.stack([e & np.uint64(0xFFFFFFFF), e >> np.uint64(32), np.full(n, ctr & 0xFFFFFFFF, np.uint64),
+                        np.full(n, ctr >> 32, np.uint64)], axis=-1)
+    key = np.stack([np.full(n, seed & 0xFFFFFFFF, np.uint64), np.full(n, seed >> 32, np.uint64)], axis=-1)
+    w = philox4x32_10(counter, key).astype(np.float64)
+    u1 = np.minimum((w[:, 0] + 0.5) * 2.0 ** -32, 1.0)
+    u2 = (w[:, 1] + 0.5) * 2.0 ** -32
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
 def pair_count(kind, h, w, k, n):
     """Number of (query pixel, candidate patch) pairs of one score evaluation."""
     d = k // 2

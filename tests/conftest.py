@@ -29,3 +29,16 @@ def load_case(path):
 def have_cuda():
     import torch
     return torch.cuda.is_available()
+
+
+def replay_ddpm_noise(seed, shape, nsteps):
+    """The Gaussian draws of `DDIM.sample(ddpm=True)` (src/models.py:62) for a golden generated from torch.manual_seed(seed):
+    every step first opens a DataLoader iterator inside the score module (one int64 draw from the global RNG for its base
+    seed, even with shuffle=False), then calls randn_like(x)."""
+    import torch
+    torch.manual_seed(int(seed))
+    out = []
+    for _ in range(nsteps):
+        torch.empty((), dtype=torch.int64).random_()
+        out.append(torch.randn(tuple(shape)))
+    return out

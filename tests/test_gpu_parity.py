@@ -93,6 +93,130 @@ def test_machine_golden(path, graph):
     assert np.max(np.abs(got - ref)) < 2e-3
 
 
+@pytest.mark.parametrize("path", golden_files("machinex"), ids=os.path.basename)
+def test_machinex_golden(path):
+    """Reference trajectories outside the (kind, scales) pattern: an IdealScoreModule backbone without a scales list (the
+    machine passes k=None, which IS ignores, idealscore.py:583) and LS with batch_size < N plus a label, where every score
+    evaluation reshuffles the DataLoader (replayed from the same torch seed: two global RNG draws per evaluation)."""
+    cd = _mods()
+    c = load_case(path)
+    kind = str(c["kind"])
+    label = None if int(c["label"]) < 0 else int(c["label"])
+    scales = [int(v) for v in c["scales"]] or None
+    nsteps = int(c["nsteps"])
+    mod = _make(kind, _dataset(c["bank"], c["labels"]), 3, int(c["batch_size"]), None)
+    machine = cd.ScheduledScoreMachine(mod, in_channels=c["x"].shape[1], imsize=c["x"].shape[-1], scales=scales,
+                                       default_time_steps=nsteps)
+    x = torch.from_numpy(c["x"]).cuda()
+    lab = None if label is None else torch.tensor([label])
+    if int(c["torch_seed"]) >= 0:
+        torch.manual_seed(int(c["torch_seed"]))
+    out = machine(x.clone(), label=lab, device=torch.device("cuda"))
+    ref = c["out"].astype(np.float64)
+    got = out.cpu().double().numpy()
+    psnr = 10 * np.log10(4.0 / max(np.mean((got - ref) ** 2), 1e-30))
+    assert psnr >= 50.0, psnr
+    assert np.max(np.abs(got - ref)) < 2e-3
+
+
+@pytest.mark.parametrize("path", golden_files("ddpm"), ids=os.path.basename)
+def test_ddpm_golden(path):
+    """Stochastic sampler against the reference's `DDIM.sample(ddpm=True)` (src/models.py:48-64) run on the reference's own
+    score module: the golden's noise (torch.randn_like from a seeded CPU generator, one draw per step) is regenerated
+    and injected; the loop starts at i = nsteps as DDIM.sample does."""
+    cd = _mods()
+    c = load_case(path)
+    kind = str(c["kind"])
+    label = None if int(c["label"]) < 0 else int(c["label"])
+    nsteps, k = int(c["nsteps"]), int(c["k"])
+    mod = _make(kind, _dataset(c["bank"], c["labels"]), k, int(c["batch_size"]), None)
+    machine = cd.ScheduledScoreMachine(mod, in_channels=c["x"].shape[1], imsize=c["x"].shape[-1], default_time_steps=nsteps)
+    from conftest import replay_ddpm_noise
+    noises = replay_ddpm_noise(c["torch_seed"], c["x"].shape, nsteps)
+    lab = None if label is None else torch.tensor([label])
+    out = machine(torch.from_numpy(c["x"]).cuda(), label=lab, device=torch.device("cuda"), ddpm=True, noise=noises,
+                  first_step=nsteps)
+    assert np.max(np.abs(out.cpu().double().numpy() - c["out"].astype(np.float64))) < 2e-3
+
+
+def test_ddpm_device_noise_stream():
+    """The Philox4x32-10 stream of the stochastic sampler: bit-compatible with the restatement in oracle/ (checked there
+    against Random123's known answers), reproducible from the seed inside and outside a captured CUDA graph, fresh per seed."""
+    import ctypes
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200 import _lib
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    cd = _mods()
+    lib = _lib.load()
+    seed, ctr, n = 0x1234ABCD5678, 5, 4096
+    so_dev = torch.tensor([seed, 2], dtype=torch.int64, device="cuda")
+    out = torch.empty(n, device="cuda")
+    _lib.check(lib.cds_randn_philox(_lib.ptr(out), n, _lib.ptr(so_dev), ctr - 2, _lib.stream_ptr()), "cds_randn_philox")
+    ref = so.philox_normal(n, seed, ctr)
+    assert np.max(np.abs(out.cpu().double().numpy() - ref)) < 1e-4
+    bank, labels = synthetic_bank(32, 3, 16, nlabels=2, seed=3)
+    mod = _make("ELS", (bank, labels), 5, 16, None)
+    x = torch.randn(2, 3, 16, 16, generator=torch.Generator().manual_seed(5)).cuda()
+    outs = {}
+    for graph in (False, True):
+        machine = cd.ScheduledScoreMachine(mod, in_channels=3, imsize=16, scales=[3, 3, 5, 5, 7], use_cuda_graph=graph)
+        outs[graph] = [machine(x, label=torch.tensor([1]), device="cuda", ddpm=True, seed=sd) for sd in (11, 11, 12)]
+        assert torch.equal(outs[graph][0], outs[graph][1])                  # same seed: same trajectory (graph replay too)
+        assert not torch.allclose(outs[graph][0], outs[graph][2])           # another seed: another one
+    assert torch.equal(outs[False][0], outs[True][0])
+    ddim = cd.ScheduledScoreMachine(mod, in_channels=3, imsize=16, scales=[3, 3, 5, 5, 7])(x, label=torch.tensor([1]), device="cuda")
+    assert not torch.allclose(ddim, outs[True][0])
+
+
+def test_full_bank_parity_at_benchmarked_size(cifar_bank):
+    """The headline configuration itself (50 000-image bank, one class = 5 063 images, the shipped CIFAR schedule, x taken
+    from a real trajectory): at the steps i = 1 (k=3, two query passes, lowest noise), 7 (k=7, two passes, just above the
+    single-pass boundary), 10 (k=7, single pass), 12 (k=9) and 19 (k=17) the denoised estimate of the tensor-core path
+    ("auto": P.V epilogue for k <= 9, FMA above) is compared with
+      (i)  the exact-fp32 SIMT kernel (cds_partials_simt) on the same x, all three channels, and
+      (ii) the CPU port of the reference (oracle/score_port.py, torch fp32) on the same 5 063-image class sub-bank.
+    Tolerance 1e-3 on mu (north_star); the worst errors go to gpurun_out/ for profiles/."""
+    from oracle import score_port as sp
+    from convolutional_diffusion_b200.scales import load_scales
+    from convolutional_diffusion_b200.selection import select
+    cd = _mods()
+    bank, labels = cifar_bank
+    scales = load_scales("CIFAR10_ResNet_zeros_conditional")
+    label, bs = 0, 64
+    mod = _make("ELS", (bank, labels), 3, bs, None, precision="auto")          # as bench.py: one query pass where allowed
+    machine = cd.ScheduledScoreMachine(mod, in_channels=3, imsize=32, scales=scales)
+    x0 = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(10_000)).cuda()
+    _, rec = machine.trajectory(x0, label=torch.tensor([label]), device="cuda")
+    exact = _make("ELS", (bank, labels), 3, bs, None, use_tensor_cores=False, bank=mod.bank)
+    eng = exact.engine("cuda")
+    sel = exact.selection(label)
+    idx, logw = select("ELS", labels.numpy(), label, bs, None)
+    sub = bank[torch.from_numpy(idx)]
+    lw = torch.from_numpy(logw).float()
+    lines, worst = [], 0.0
+    for r in rec:
+        if r["i"] not in (1, 7, 10, 12, 19):
+            continue
+        mu_tc = r["mu"][0].cpu().double().numpy()
+        mu = torch.empty_like(r["x"])
+        eng.evaluate("ELS", r["x"].contiguous(), torch.full((1,), r["beta"], device="cuda"), r["k"], sel,
+                     query_pad="circular", mu=mu, beta_min=r["beta"])
+        e_simt = float(np.max(np.abs(mu_tc - mu[0].cpu().double().numpy())))
+        mu_p = sp.els_mu(r["x"][0].cpu(), sub, r["beta"], r["k"], lw)
+        e_port = float(np.max(np.abs(mu_tc - mu_p.double().numpy())))
+        e_ref = float(np.max(np.abs(mu[0].cpu().double().numpy() - mu_p.double().numpy())))
+        lines.append(f"i={r['i']:2d} k={r['k']:2d} beta={r['beta']:.5f} passes={mod.engine('cuda').passes_for(r['k'], r['beta'])}: "
+                     f"tensor-core vs exact SIMT {e_simt:.2e}, vs CPU port {e_port:.2e} (SIMT vs port {e_ref:.2e})")
+        worst = max(worst, e_simt, e_port)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "full_bank_parity.log"), "w") as f:
+        f.write("\n".join(lines) + f"\nworst {worst:.2e} (tolerance 1e-3)\n")
+    print("\n".join(lines))
+    assert len(lines) == 5
+    assert worst < MU_TOL, lines
+
+
 def _oracle_mu(kind, x, bank, labels, label, beta, k, bs, ms=None):
     from oracle import score_oracle as so
     h = x.shape[-1]
