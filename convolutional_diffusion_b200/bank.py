@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .selection import select, shard
+from .selection import assign_ranks, select, shard
 
 
 def dataset_to_tensors(dataset):
@@ -49,7 +49,12 @@ def dataset_to_tensors(dataset):
 
 
 class PatchBank:
-    def __init__(self, images, labels, device=None):
+    """rank / world: bank sharding across the GPUs of one box.  The rank keeps (uploads, packs, streams) only the images it
+    owns under selection.assign_ranks -- about N/world of them -- while the labels of the whole dataset stay on the host,
+    because the reference's DataLoader bookkeeping (which images take part, with which weight) is defined on the whole
+    dataset."""
+
+    def __init__(self, images, labels, device=None, rank=0, world=1):
         self.lib = _lib.load()                                   # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("PatchBank needs a CUDA device: the score machines have no CPU fallback")
@@ -59,10 +64,20 @@ class PatchBank:
         if self.device.index is None:                            # always a concrete ordinal: tensors report cuda:N
             self.device = torch.device("cuda", torch.cuda.current_device())
         assert images.dim() == 4, "bank images must be [N,C,H,W]"
-        self.images = images.to(self.device, torch.float32).contiguous()
         self.labels = np.asarray(torch.as_tensor(labels).cpu()).astype(np.int64).reshape(-1)
-        self.N, self.C, self.H, self.W = self.images.shape
+        self.N = int(images.shape[0])                            # images of the whole dataset (selection bookkeeping)
         assert self.labels.shape[0] == self.N
+        self.rank, self.world = int(rank), int(world)
+        self.owner = assign_ranks(self.labels, self.world)
+        if self.world > 1:
+            mine = np.nonzero(self.owner == self.rank)[0]
+            self.local_of = np.full(self.N, -1, dtype=np.int64)  # dataset index -> index in this rank's device arrays
+            self.local_of[mine] = np.arange(mine.shape[0])
+            images = images[torch.from_numpy(mine)]
+        else:
+            self.local_of = None
+        self.images = images.to(self.device, torch.float32).contiguous()
+        self.N_local, self.C, self.H, self.W = self.images.shape
         self._strip = None
         self._rows8 = None
         self._pnorm = {}
@@ -78,14 +93,14 @@ class PatchBank:
                 exact8 = bool(((v - v.round()).abs().max() < 1e-3).item()) and bool((v.min() > -0.5).item()) \
                     and bool((v.max() < 255.5).item())
                 scale = 255.0 if exact8 else 256.0
-                n = self.N * self.C * self.H * self.W
+                n = self.N_local * self.C * self.H * self.W
                 hi = torch.empty(n * 8, dtype=torch.float16, device=self.device)
-                _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
+                _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N_local, self.C, self.H, self.W,
                                                     scale, 0, _lib.ptr(hi), _lib.stream_ptr()), "cds_pack_strip8")
                 lo = None
                 if not exact8:
                     lo = torch.empty(n * 8, dtype=torch.float16, device=self.device)
-                    _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
+                    _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N_local, self.C, self.H, self.W,
                                                         scale, 1, _lib.ptr(lo), _lib.stream_ptr()), "cds_pack_strip8")
                 self._strip = (hi, lo, scale)
         return self._strip
@@ -98,8 +113,8 @@ class PatchBank:
             return None
         if self._rows8 is None:
             with torch.cuda.device(self.device):
-                out = torch.empty(self.N * self.C * self.H * self.W * 8, dtype=torch.float16, device=self.device)
-                _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N, self.C, self.H, self.W,
+                out = torch.empty(self.N_local * self.C * self.H * self.W * 8, dtype=torch.float16, device=self.device)
+                _lib.check(self.lib.cds_pack_strip8(_lib.ptr(self.images), self.N_local, self.C, self.H, self.W,
                                                     scale, 2, _lib.ptr(out), _lib.stream_ptr()), "cds_pack_strip8")
                 self._rows8 = out
         return self._rows8
@@ -108,8 +123,8 @@ class PatchBank:
         """||p||^2 of every valid k x k x C patch, [N, (H-k+1)*(W-k+1)] fp32 (computed once per k)."""
         if k not in self._pnorm:
             with torch.cuda.device(self.device):
-                out = torch.empty(self.N * (self.H - k + 1) * (self.W - k + 1), dtype=torch.float32, device=self.device)
-                _lib.check(self.lib.cds_patch_norms(_lib.ptr(self.images), self.N, self.C, self.H, self.W, k,
+                out = torch.empty(self.N_local * (self.H - k + 1) * (self.W - k + 1), dtype=torch.float32, device=self.device)
+                _lib.check(self.lib.cds_patch_norms(_lib.ptr(self.images), self.N_local, self.C, self.H, self.W, k,
                                                     _lib.ptr(out), _lib.stream_ptr()), "cds_patch_norms")
                 self._pnorm[k] = out
         return self._pnorm[k]
@@ -118,23 +133,30 @@ class PatchBank:
         """fp16 [N,H,W,8] norm plane of kernel size k for the tensor-core kernel (computed once per k)."""
         if k not in self._nplane:
             with torch.cuda.device(self.device):
-                out = torch.empty(self.N * self.H * self.W * 8, dtype=torch.float16, device=self.device)
-                _lib.check(self.lib.cds_pack_norm_plane(_lib.ptr(self.images), self.N, self.C, self.H, self.W, k,
+                out = torch.empty(self.N_local * self.H * self.W * 8, dtype=torch.float16, device=self.device)
+                _lib.check(self.lib.cds_pack_norm_plane(_lib.ptr(self.images), self.N_local, self.C, self.H, self.W, k,
                                                         _lib.ptr(out), _lib.stream_ptr()), "cds_pack_norm_plane")
                 self._nplane[k] = out
         return self._nplane[k]
 
+    def ls_bytes_per_pixel(self):
+        """Bytes per bank pixel the LS kernels stream from HBM (algorithmic bytes of the roofline)."""
+        return 4
+
     # ---- selection -----------------------------------------------------------------------------
-    def selection(self, kind, label, batch_size, max_samples, order=None, rank=0, world=1):
-        """(idx int32 device, logw fp32 device, n_sel) for one score evaluation; cached per key when the
-        visiting order is the identity."""
-        key = (kind, label, batch_size, max_samples, rank, world) if order is None else None
+    def selection(self, kind, label, batch_size, max_samples, order=None):
+        """(idx int32 device, logw fp32 device, n_sel) for one score evaluation: the reference's DataLoader bookkeeping on the
+        whole dataset, then -- with a sharded bank -- the part owned by this rank, as indices into its device arrays.
+        Cached per key when the visiting order is the identity."""
+        key = (kind, label, batch_size, max_samples) if order is None else None
         if key is not None and key in self._sel:
             return self._sel[key]
         idx, logw = select(kind, self.labels, label, batch_size, max_samples, order)
         if idx.shape[0] == 0:
             raise RuntimeError(f"no bank image selected (kind={kind}, label={label}, max_samples={max_samples})")
-        idx, logw = shard(idx, logw, rank, world)
+        if self.world > 1:
+            idx, logw = shard(idx, logw, self.rank, self.world, self.owner)
+            idx = self.local_of[idx]
         out = (torch.from_numpy(idx.astype(np.int32)).to(self.device),
                torch.from_numpy(logw.astype(np.float32)).to(self.device), int(idx.shape[0]))
         if key is not None:

@@ -72,6 +72,18 @@ def allgather_packed(engine, P, local_S):
     return gathered, world
 
 
+def shared_order(order, group, device=None):
+    """The DataLoader visiting order every rank must use when the bank is sharded and the order is drawn from the global
+    torch RNG (LS hard-codes shuffle=True, idealscore.py:489): each rank has consumed its own two RNG draws, as one
+    reference evaluation does; rank 0's permutation is broadcast so that all ranks split the same selection."""
+    import numpy as np
+    t = torch.from_numpy(np.array(order, dtype=np.int64))          # a copy: the broadcast must not overwrite the caller's draw
+    if dist.get_backend(group) == "nccl":
+        t = t.to(device)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0), group=group)
+    return t.cpu().numpy()
+
+
 def init_from_env():
     """One process per GPU (torchrun): returns (rank, world, local_rank) and initialises NCCL if world > 1."""
     import os
@@ -84,3 +96,33 @@ def init_from_env():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
     return rank, world, local
+
+
+def shutdown(timeout_s=30.0):
+    """Orderly teardown of a multi-rank run whose trajectories were captured in CUDA graphs: the graphs reference the NCCL
+    communicator (the all-gathers are captured nodes), and destroying the communicator while such graphs are alive -- or
+    leaving both to interpreter shutdown in arbitrary order -- can block forever.  Callers first drop their graphs
+    (ScheduledScoreMachine.release_graphs), then call this: drain the device, agree that every rank is done, destroy
+    the group.  A watchdog turns a blocked destructor into a hard exit instead of a hung job (it has never fired in the
+    runs of round 2; it is there because a hang on a shared GPU box is worse than a missing destructor)."""
+    import os
+    import threading
+    if not dist.is_initialized():
+        return
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    done = threading.Event()
+
+    def _watchdog():
+        if not done.wait(timeout_s):
+            import sys
+            sys.stderr.write("convolutional_diffusion_b200.distributed.shutdown: process group teardown blocked, exiting hard\n")
+            sys.stderr.flush()
+            os._exit(0)
+
+    threading.Thread(target=_watchdog, daemon=True).start()
+    dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.destroy_process_group()
+    done.set()

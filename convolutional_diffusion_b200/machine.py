@@ -231,6 +231,14 @@ class ScheduledScoreMachine(nn.Module):
             graph.replay()
             return xs.clone()
 
+    def release_graphs(self):
+        """Drops every captured trajectory graph (and the static buffers they own).  With a sharded bank the graphs hold
+        captured NCCL all-gathers: release them before the process group is destroyed (distributed.shutdown)."""
+        if self._graphs:
+            torch.cuda.synchronize()
+            self._graphs.clear()
+            torch.cuda.synchronize()
+
     def trajectory(self, x, nsteps=None, label=None, device=None):
         """Runs the native loop eagerly and returns (final x, per-step records of x / mu) -- used by the parity
         tests, which check the denoised estimate at every step."""

@@ -91,7 +91,10 @@ class _ScoreModuleBase(nn.Module):
         if self._engine is None:
             if self._bank is None:
                 images, labels = dataset_to_tensors(self.dataset)
-                self._bank = PatchBank(images, labels, device=device)
+                rank, world = self._rank_world()
+                self._bank = PatchBank(images, labels, device=device, rank=rank, world=world)
+            elif (self._bank.rank, self._bank.world) != self._rank_world():
+                raise RuntimeError("bank= was built for another sharding (rank/world) than this module's process_group")
             self._engine = ScoreEngine(self._bank, precision=self.precision,
                                        use_tensor_cores=self.use_tensor_cores, group=self.process_group)
         return self._engine
@@ -114,16 +117,11 @@ class _ScoreModuleBase(nn.Module):
         if self.shuffle or kind == "LS" and self._ls_shuffles():
             order = dataloader_shuffle_order(eng.bank.N)
             if world > 1:
-                # every rank must slice the SAME permutation: rank r takes order[r::world], so ranks whose global RNG
-                # states differ would otherwise count some images twice and drop others.  Rank 0's draw wins (each rank
-                # still consumes its own two RNG draws, as one reference evaluation does).
-                import torch.distributed as dist
-                t = torch.from_numpy(order.astype("int64"))
-                if dist.get_backend(self.process_group) == "nccl":
-                    t = t.to(eng.device)
-                dist.broadcast(t, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
-                order = t.cpu().numpy()
-        return eng.bank.selection(kind, label, self.batch_size, self.max_samples, order, rank, world)
+                # every rank must split the SAME visiting order: ranks whose global RNG states differ would otherwise count
+                # some images twice and drop others.  Rank 0's draw wins (distributed.shared_order).
+                from .distributed import shared_order
+                order = shared_order(order, self.process_group, eng.device)
+        return eng.bank.selection(kind, label, self.batch_size, self.max_samples, order)
 
     def _ls_shuffles(self):
         """LS hard-codes shuffle=True (idealscore.py:489); the order only matters when batches end up with

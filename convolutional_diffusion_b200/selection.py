@@ -19,7 +19,7 @@ import math
 
 import numpy as np
 
-__all__ = ["select", "shard", "dataloader_shuffle_order"]
+__all__ = ["select", "shard", "assign_ranks", "dataloader_shuffle_order"]
 
 
 def select(kind, labels, label, batch_size, max_samples, order=None):
@@ -59,10 +59,31 @@ def select(kind, labels, label, batch_size, max_samples, order=None):
     return idx.astype(np.int64), logw
 
 
-def shard(idx, logw, rank, world):
-    """Interleaved bank shard of one rank: keeps conditional subsets balanced and needs no data-path
-    collective -- every rank reduces its slice to (max, sum-exp, weighted-sum) partials."""
-    return idx[rank::world], logw[rank::world]
+def assign_ranks(labels, world):
+    """Owner rank of every bank image for bank sharding: the q-th image of its class (in dataset order) belongs to rank
+    q % world.  The assignment depends on the image only -- not on the selection -- so a rank uploads and packs just the
+    ~N/world images it owns, and every selection (any label, max_samples, visiting order) is split into the subsets
+    of its images owned by each rank: balanced per class, hence balanced for conditional and unconditional runs alike."""
+    labels = np.asarray(labels)
+    owner = np.zeros(labels.shape[0], dtype=np.int64)
+    if world <= 1:
+        return owner
+    order = np.argsort(labels, kind="stable")
+    sorted_labels = labels[order]
+    first = np.r_[0, np.nonzero(np.diff(sorted_labels))[0] + 1]            # start of every class run
+    start_of = np.repeat(first, np.diff(np.r_[first, labels.shape[0]]))
+    owner[order] = (np.arange(labels.shape[0]) - start_of) % world
+    return owner
+
+
+def shard(idx, logw, rank, world, owner=None):
+    """The part of a selection that lives on `rank`: its images owned by that rank (assign_ranks), in selection order; the
+    log-weights travel with the images.  No data-path collective is needed -- every rank reduces its part to
+    (max, sum-exp, weighted-sum) partials.  Without `owner` the selection is dealt out round robin (idx[rank::world])."""
+    if owner is None:
+        return idx[rank::world], logw[rank::world]
+    keep = owner[idx] == rank
+    return idx[keep], logw[keep]
 
 
 def dataloader_shuffle_order(n):

@@ -25,7 +25,9 @@ def main():
         full = cls((bank, labels), **kw)
         shard = cls((bank, labels), process_group=dist.group.WORLD, **kw)
         for label in (None, torch.tensor([4])):
+            torch.manual_seed(11)        # LS reshuffles its DataLoader per call (idealscore.py:489): same draws for both
             s0 = full(torch.full((2,), t), x, label=label, device=dev)
+            torch.manual_seed(11)
             s1 = shard(torch.full((2,), t), x, label=label, device=dev)
             err = float((s0 - s1).abs().max())
             worst = max(worst, err)
@@ -45,17 +47,29 @@ def main():
     full = LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=64, schedule=cosine_noise_schedule)
     shard = LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=64, schedule=cosine_noise_schedule,
                                   process_group=dist.group.WORLD)
-    o0 = ScheduledScoreMachine(full, scales=scales)(x, label=torch.tensor([2]), device=dev)
-    o1 = ScheduledScoreMachine(shard, scales=scales)(x, label=torch.tensor([2]), device=dev)
+    m0, m1 = ScheduledScoreMachine(full, scales=scales), ScheduledScoreMachine(shard, scales=scales)
+    o0 = m0(x, label=torch.tensor([2]), device=dev)
+    o1 = m1(x, label=torch.tensor([2]), device=dev)
+    o1b = m1(x, label=torch.tensor([2]), device=dev)          # graph replay with the captured all-gathers
+    assert torch.equal(o1, o1b)
+    # every rank holds only the images it owns
+    nloc = shard.bank.N_local
+    assert abs(nloc - 3000 / world) <= 10, nloc
     err = float((o0 - o1).abs().max())
     assert err < 1e-3, err
     gathered = [torch.empty_like(o1) for _ in range(world)]
     dist.all_gather(gathered, o1)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "x diverged across ranks"
     if rank == 0:
-        print(f"dist check ok: world={world} worst score diff {worst:.2e}, trajectory diff {err:.2e}, ranks bit-identical")
-    dist.barrier()
-    dist.destroy_process_group()
+        print(f"dist check ok: world={world} worst score diff {worst:.2e}, trajectory diff {err:.2e}, ranks bit-identical, "
+              f"{nloc} of 3000 images resident per rank")
+    # orderly teardown: graphs (captured NCCL nodes) first, then the process group -- no os._exit
+    from convolutional_diffusion_b200.distributed import shutdown
+    m0.release_graphs()
+    m1.release_graphs()
+    shutdown()
+    if rank == 0:
+        print("teardown ok")
 
 
 if __name__ == "__main__":

@@ -52,7 +52,9 @@ def _worker(rank, world, port, out):
     labels = rng.integers(0, 3, n)
     x = rng.normal(size=(c, h, h))
     idx, logw = sel.select("LS", labels, label, bs, None)
-    my_idx, my_logw = sel.shard(idx, logw, rank, world)
+    owner = sel.assign_ranks(labels, world)              # bank sharding by image ownership: each rank holds ~N/world images
+    my_idx, my_logw = sel.shard(idx, logw, rank, world, owner)
+    assert set(my_idx.tolist()) <= set(np.nonzero(owner == rank)[0].tolist())
     m, l, acc = _partials_ls(x, bank[my_idx], beta, k, my_logw)
     B, HW = 1, h * h
     gm, gl, gacc = gather_partials(torch.from_numpy(m).reshape(B, HW), torch.from_numpy(l).reshape(B, HW),
@@ -75,3 +77,33 @@ def test_sharded_partials_merge_to_full_result():
     assert len(out) == world
     for r in range(world):
         assert out[r] < 1e-10, out[r]
+
+
+def _worker_order(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from convolutional_diffusion_b200.distributed import shared_order
+    torch.manual_seed(100 + rank)                       # ranks with DIFFERENT global RNG states
+    mine = sel.dataloader_shuffle_order(53)
+    order = shared_order(mine, dist.group.WORLD)
+    out[rank] = (mine.tolist(), order.tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shuffled_selection_uses_one_order_on_all_ranks():
+    """Bank sharding + a shuffled DataLoader order (LS, shuffle=True): ranks seeded differently draw different permutations;
+    the shared order is rank 0's on every rank, so the shards partition one selection (no image twice, none dropped)."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_order, args=(world, port, out), nprocs=world, join=True)
+    assert out[0][0] != out[1][0]                        # the local draws differ ...
+    assert out[0][1] == out[1][1] == out[0][0]           # ... the shared order is rank 0's
+    labels = np.random.default_rng(1).integers(0, 3, 53)
+    owner = sel.assign_ranks(labels, world)
+    idx, logw = sel.select("LS", labels, 1, 8, None, np.asarray(out[0][1]))
+    parts = [sel.shard(idx, logw, r, world, owner)[0] for r in range(world)]
+    assert sorted(np.concatenate(parts).tolist()) == sorted(idx.tolist())

@@ -43,6 +43,31 @@ def test_shard_partition():
     assert max(len(s) for s in seen) - min(len(s) for s in seen) <= 1
 
 
+def test_rank_ownership_is_a_balanced_partition_of_every_selection():
+    """Bank sharding by image ownership (selection.assign_ranks): the owner depends on the image only, every selection
+    -- conditional, unconditional, with max_samples, shuffled -- is partitioned by it, and the parts are balanced per class
+    (sizes differ by at most one) so that no rank idles in a class-conditional run."""
+    rng = np.random.default_rng(3)
+    labels = rng.integers(0, 10, 5003)
+    for world in (2, 4, 8):
+        owner = sel.assign_ranks(labels, world)
+        assert owner.min() == 0 and owner.max() == world - 1
+        for c in range(10):
+            counts = np.bincount(owner[labels == c], minlength=world)
+            assert counts.max() - counts.min() <= 1, (world, c, counts)
+        for kind, label, bs, ms, order in (("ELS", 4, 64, None, None), ("ELS", None, 64, 3000, None),
+                                           ("LS", 7, 256, None, rng.permutation(5003)), ("bbELS", None, 64, None, None)):
+            idx, logw = sel.select(kind, labels, label, bs, ms, order)
+            parts = [sel.shard(idx, logw, r, world, owner) for r in range(world)]
+            assert np.array_equal(np.sort(np.concatenate([p[0] for p in parts])), np.sort(idx))
+            for pi, pw in parts:
+                pos = {int(v): q for q, v in enumerate(idx)}
+                assert np.allclose(pw, logw[[pos[int(v)] for v in pi]])        # log-weights travel with their images
+            if ms is None and order is None:
+                sizes = [len(p[0]) for p in parts]
+                assert max(sizes) - min(sizes) <= (10 if label is None else 1), (kind, label, sizes)
+    assert np.array_equal(sel.assign_ranks(labels, 1), np.zeros(5003, dtype=np.int64))
+
 def test_shuffle_order_matches_dataloader():
     """LS hard-codes shuffle=True (idealscore.py:489): reproduce the DataLoader's permutation for a given
     global RNG state."""
