@@ -28,6 +28,7 @@ SIGNATURES = {
     "cds_patch_norms": (_i, [_p, _i64, _i, _i, _i, _i, _p, _p]),
     "cds_pack_norm_plane": (_i, [_p, _i64, _i, _i, _i, _i, _p, _p]),
     "cds_partials_simt": (_i, [_i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
+    "cds_score_vjp_simt": (_i, [_i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "cds_ls_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_ls_rows_supported": (_i, [_i, _i, _i, _i]),
     "cds_ls_rows_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),

@@ -124,6 +124,146 @@ __global__ void __launch_bounds__(SIMT_THREADS) partials_simt_kernel(SimtParams 
   }
 }
 
+// Vector-Jacobian product of mu with respect to x in the same unified form (the reference callers differentiate the score
+// modules with autograd: src/utils/exterior_derivative.py:68-79, scripts/analyze_exterior_derivative.py:171-183).  With
+// normalised weights w_p = exp2(t_p - m)/l of the FINAL merged state and h_p = sum_c g_c (v_p[c] - mu_c),
+//   d mu_c / d q_e = (a/beta) sum_p w_p (v_p[c] - mu_c) p_e        (the q_e term cancels because sum_p w_p (v_p - mu) = 0)
+// so the gradient that query pixel (i,j) sends to the patch element e = (c', dy, dx) of its padded patch is
+//   G[e] = (a/beta) sum_p w_p h_p p_e,
+// scattered to x[c', i+dy-d, j+dx-d] (wrapped for circular padding, dropped where the patch element is zero padding).
+// One thread per query pixel; per bank image and candidate row u: (1) coefficients w_p h_p of the row's candidates from the
+// exact distances, kept in registers; (2) for every patch row (c', dy) the correlation of those coefficients with the bank
+// row, accumulated in a shared-memory array G[e][thread].  The caller adds -g/beta and the factor a/beta of the score.
+struct VjpParams {
+  int kind, pad, B, C, H, W, k, splits, tpb;
+  long long n_sel;
+  const float* x;
+  const float* beta;
+  const float* images;
+  const int32_t* idx;
+  const float* logw;
+  const float *m, *l, *mu, *g;
+  float* grad;
+};
+
+constexpr int VJP_MAXROW = 64;     // candidates per row kept in registers (images up to 64 + ... pixels wide)
+
+template <int C>
+__global__ void __launch_bounds__(128) score_vjp_simt_kernel(VjpParams p) {
+  extern __shared__ float smem[];
+  const int H = p.H, W = p.W, k = p.k, d = k / 2, TPB = p.tpb;
+  const int Hp = H + 2 * d, Wp = W + 2 * d, plane = Hp * Wp, Dk = C * k * k;
+  float* xs = smem;               // [C][Hp][Wp] padded query
+  float* ts = smem + C * plane;   // [C][Hp][Wp] zero-padded bank image
+  float* G = ts + C * plane;      // [Dk][TPB]
+  const int b = blockIdx.z, split = blockIdx.y, tid = threadIdx.x;
+  const int pix = blockIdx.x * TPB + tid;
+  const bool active = pix < H * W;
+  const int i = active ? pix / W : 0, j = active ? pix % W : 0;
+  const float beta = p.beta[b];
+  const float a = sqrtf(1.f - beta);
+  const float sc = -CDS_LOG2E / (2.f * beta);
+  const float* xb = p.x + (size_t)b * C * H * W;
+  for (int e = tid; e < C * plane; e += TPB) {
+    int c = e / plane, r = e % plane, y = r / Wp - d, xx = r % Wp - d;
+    float v = 0.f;
+    if (p.pad == CDS_PAD_CIRCULAR) {
+      y = (y % H + H) % H;
+      xx = (xx % W + W) % W;
+      v = xb[(c * H + y) * W + xx];
+    } else if (y >= 0 && y < H && xx >= 0 && xx < W) {
+      v = xb[(c * H + y) * W + xx];
+    }
+    xs[e] = v;
+    ts[e] = 0.f;
+  }
+  for (int e = tid; e < Dk * TPB; e += TPB) G[e] = 0.f;
+  int u0, u1, v0, v1;
+  if (p.kind == CDS_KIND_LS) {
+    u0 = i; u1 = i + 1; v0 = j; v1 = j + 1;
+  } else if (p.kind == CDS_KIND_ELS) {
+    u0 = d; u1 = H - d; v0 = d; v1 = W - d;
+  } else {
+    const bool rb = (i < d) || (i >= H - d), cb = (j < d) || (j >= W - d);
+    u0 = rb ? i : d; u1 = rb ? i + 1 : H - d;
+    v0 = cb ? j : d; v1 = cb ? j + 1 : W - d;
+  }
+  const int HW = H * W;
+  float mq = 0.f, inv_l = 0.f, muq[C], gq[C];
+  if (active) {
+    mq = p.m[(size_t)b * HW + pix];
+    inv_l = 1.f / p.l[(size_t)b * HW + pix];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      muq[c] = p.mu[((size_t)b * C + c) * HW + pix];
+      gq[c] = p.g[((size_t)b * C + c) * HW + pix];
+    }
+  }
+  const long long n0 = p.n_sel * split / p.splits, n1 = p.n_sel * (split + 1) / p.splits;
+  for (long long n = n0; n < n1; ++n) {
+    __syncthreads();
+    const float* img = p.images + (size_t)p.idx[n] * C * H * W;
+    for (int e = tid; e < C * H * W; e += TPB) {
+      int c = e / (H * W), r = e % (H * W), y = r / W, xx = r % W;
+      ts[c * plane + (y + d) * Wp + xx + d] = __ldg(img + e);
+    }
+    __syncthreads();
+    if (!active) continue;
+    const float lw = p.logw[n] * CDS_LOG2E;
+    for (int u = u0; u < u1; ++u) {
+      float coef[VJP_MAXROW];
+      // (1) w_p h_p of the candidates (u, v0..v1)
+      for (int v = v0; v < v1; ++v) {
+        float dist = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float* xr = xs + c * plane + i * Wp + j;
+          const float* tr = ts + c * plane + u * Wp + v;
+          float cs = 0.f;
+          for (int dy = 0; dy < k; ++dy) {
+            float rs = 0.f;
+            for (int dx = 0; dx < k; ++dx) {
+              float df = fmaf(-a, tr[dy * Wp + dx], xr[dy * Wp + dx]);
+              rs = fmaf(df, df, rs);
+            }
+            cs += rs;
+          }
+          dist += cs;
+        }
+        float h = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) h = fmaf(gq[c], ts[c * plane + (u + d) * Wp + v + d] - muq[c], h);
+        coef[v - v0] = exp2f(fmaf(dist, sc, lw) - mq) * inv_l * h;
+      }
+      // (2) G[c', dy, dx] += sum_v coef[v] * T[c'][u - d + dy][v - d + dx]   (padded coordinates: ts[..][u + dy][v + dx])
+      for (int c = 0; c < C; ++c)
+        for (int dy = 0; dy < k; ++dy) {
+          const float* tr = ts + c * plane + (u + dy) * Wp;
+          for (int dx = 0; dx < k; ++dx) {
+            float s2 = 0.f;
+            for (int v = v0; v < v1; ++v) s2 = fmaf(coef[v - v0], tr[v + dx], s2);
+            G[((c * k + dy) * k + dx) * TPB + tid] += s2;
+          }
+        }
+    }
+  }
+  if (!active) return;
+  const float ab = a / beta;
+  float* gb = p.grad + (size_t)b * C * HW;
+  for (int c = 0; c < C; ++c)
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        int y = i + dy - d, xx = j + dx - d;
+        if (p.pad == CDS_PAD_CIRCULAR) {
+          y = (y % H + H) % H;
+          xx = (xx % W + W) % W;
+        } else if (y < 0 || y >= H || xx < 0 || xx >= W) {
+          continue;                    // zero padding: a constant, no gradient
+        }
+        atomicAdd(gb + (c * H + y) * W + xx, ab * G[((c * k + dy) * k + dx) * TPB + tid]);
+      }
+}
+
 __global__ void pack_strip8_kernel(const float* __restrict__ images, long long N, int C, int H, int W, float scale,
                                    int plane, uint4* __restrict__ out) {
   const long long total = N * C * H * W;
@@ -467,5 +607,38 @@ extern "C" int cds_randn_philox(float* out, int64_t n, const uint64_t* seed_offs
   randn_philox_kernel<<<(int)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       out, (long long)n, (const unsigned long long*)seed_offset, step);
   CDS_CHECK_LAUNCH("randn_philox_kernel");
+  return CDS_OK;
+}
+
+extern "C" int cds_score_vjp_simt(int kind, int query_pad, const float* x, int B, int C, int H, int W, int k,
+                                  const float* beta, const float* images, const int32_t* idx, const float* logw,
+                                  int64_t n_sel, int splits, const float* m, const float* l, const float* mu,
+                                  const float* g, float* grad_mu, void* stream) {
+  CDS_CHECK_ARG(kind >= 0 && kind <= 2, "cds_score_vjp_simt: bad kind %d", kind);
+  CDS_CHECK_ARG(C >= 1 && C <= 4, "cds_score_vjp_simt: C=%d unsupported (1..4)", C);
+  CDS_CHECK_ARG(k >= 1 && (k & 1), "cds_score_vjp_simt: k=%d must be odd", k);
+  CDS_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && n_sel >= 1 && splits >= 1, "cds_score_vjp_simt: empty problem");
+  CDS_CHECK_ARG(W - k + 1 <= VJP_MAXROW || kind == CDS_KIND_LS, "cds_score_vjp_simt: more than %d candidates per row", VJP_MAXROW);
+  if (kind == CDS_KIND_ELS) CDS_CHECK_ARG(k <= H && k <= W, "cds_score_vjp_simt: ELS needs k <= H,W");
+  if (splits > n_sel) splits = (int)n_sel;
+  const int d = k / 2;
+  const size_t planes = (size_t)2 * C * (H + 2 * d) * (W + 2 * d) * sizeof(float);
+  int tpb = 128;
+  while (tpb > 32 && planes + (size_t)C * k * k * tpb * sizeof(float) > 200 * 1024) tpb >>= 1;
+  const size_t smem = planes + (size_t)C * k * k * tpb * sizeof(float);
+  CDS_CHECK_ARG(smem <= 227 * 1024, "cds_score_vjp_simt: geometry too large for shared memory (%zu B)", smem);
+  VjpParams p{kind, query_pad, B, C, H, W, k, splits, tpb, (long long)n_sel, x, beta, images, idx, logw, m, l, mu, g, grad_mu};
+  dim3 grid((H * W + tpb - 1) / tpb, splits, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(CC)                                                                                              \
+  case CC:                                                                                                      \
+    cudaFuncSetAttribute(score_vjp_simt_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    score_vjp_simt_kernel<CC><<<grid, tpb, smem, st>>>(p);                                                      \
+    break;
+  switch (C) {
+    LAUNCH(1) LAUNCH(2) LAUNCH(3) LAUNCH(4)
+  }
+#undef LAUNCH
+  CDS_CHECK_LAUNCH("score_vjp_simt_kernel");
   return CDS_OK;
 }

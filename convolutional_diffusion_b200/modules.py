@@ -61,6 +61,48 @@ def _label_groups(label, B):
     return groups if len(groups) > 1 else None
 
 
+class _DifferentiableScore(torch.autograd.Function):
+    """score(x) with a closed-form backward (cds_score_vjp_simt), so that callers which differentiate the score modules
+    with autograd -- the exterior-derivative analysis, src/utils/exterior_derivative.py:68-79 and
+    scripts/analyze_exterior_derivative.py:171-183 -- work on the CUDA path.  Forward and backward use the exact-fp32 SIMT
+    kernels (one consistent set of softmax statistics); not differentiable twice."""
+
+    @staticmethod
+    def forward(ctx, x, eng, kind, pad, beta, k, sel):
+        from . import _lib
+        with torch.cuda.device(eng.device):
+            P = eng.combine(eng.simt_partials(kind, pad, x, beta, k, sel, tag="grad"))
+            mu, score = torch.empty_like(x), torch.empty_like(x)
+            eng.finalize(P, x, beta, mu, score)
+            ctx.save_for_backward(x, beta, P.m[0].clone(), P.l[0].clone(), mu)
+        ctx.args = (eng, kind, pad, k, sel)
+        return score
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        from . import _lib
+        x, beta, m, l, mu = ctx.saved_tensors
+        eng, kind, pad, k, sel = ctx.args
+        idx, logw, n_sel = sel
+        b = eng.bank
+        g = g.contiguous().float()
+        grad_mu = torch.zeros_like(x)
+        with torch.cuda.device(eng.device):
+            if n_sel > 0:
+                S = eng._splits((b.H * b.W + 127) // 128, x.shape[0], n_sel, waves=4, min_images=8)
+                _lib.check(eng.lib.cds_score_vjp_simt(_lib.KIND[kind], _lib.PAD[pad], _lib.ptr(x), x.shape[0], b.C, b.H, b.W, k,
+                                                      _lib.ptr(beta), _lib.ptr(b.images), _lib.ptr(idx), _lib.ptr(logw), n_sel, S,
+                                                      _lib.ptr(m), _lib.ptr(l), _lib.ptr(mu), _lib.ptr(g), _lib.ptr(grad_mu),
+                                                      _lib.stream_ptr()), "cds_score_vjp_simt")
+                eng.launches += 1
+            if eng.group is not None:                      # every rank holds the contributions of its own bank slice
+                import torch.distributed as dist
+                dist.all_reduce(grad_mu, group=eng.group)
+        bb = beta.view(-1, 1, 1, 1)
+        return -g / bb + (torch.sqrt(1 - bb) / bb) * grad_mu, None, None, None, None, None, None
+
+
 class _ScoreModuleBase(nn.Module):
     kind = None
     query_pad = None
@@ -157,10 +199,53 @@ class _ScoreModuleBase(nn.Module):
         sel_ls = None
         if self.kind == "bbELS" and k >= xd.shape[-2]:
             sel_ls = self.selection(lab, kind="LS")
+        if xd.requires_grad and torch.is_grad_enabled():
+            # autograd through the module (exterior-derivative callers): exact-fp32 forward + closed-form backward
+            kind, kk, pad = self.kind, k, (self.query_pad or "zeros")
+            if kind == "IS":
+                kind, kk, pad = "LS", 2 * max(eng.bank.H, eng.bank.W) - 1, "zeros"
+            elif kind == "bbELS" and k >= eng.bank.H:
+                kind, sel, pad = "LS", sel_ls, "zeros"
+            elif kind == "LS":
+                pad = "zeros"
+            return _DifferentiableScore.apply(xd, eng, kind, pad, beta, kk, sel)
         score = torch.empty_like(xd)
         eng.evaluate(self.kind, xd, beta, k, sel, query_pad=self.query_pad, mu=None, score=score,
                      beta_min=float(beta_cpu.min()), sel_ls=sel_ls)
         return score
+
+
+    def forward_multi_k(self, t, x, kernelsizes, label=None, device=None):
+        """The scores of the SAME (t, x) for several kernel sizes, [len(kernelsizes), B, C, H, W]: what one step of the
+        kernel-size calibration needs (scripts/scales_calibration.py:151 calls one module per size).  x is uploaded, the
+        noise levels are formed and the bank selection (label filter, log-weights) is resolved once for all sizes; the
+        per-size launches follow each other on the stream with no host synchronisation in between, and B samples share
+        every pass over the bank."""
+        if device is None:
+            device = torch.device("cuda")
+        eng = self.engine(torch.device(device))
+        xd = x.to(eng.device, torch.float32).contiguous()
+        tt = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+        if tt.numel() == 1 and xd.shape[0] > 1:
+            tt = tt.expand(xd.shape[0])
+        groups = _label_groups(label, xd.shape[0])
+        out = torch.empty((len(kernelsizes),) + tuple(xd.shape), dtype=torch.float32, device=eng.device)
+        if groups is not None:                   # per-sample labels: one pass per distinct label
+            for lab_g, rows in groups.items():
+                sel_rows = torch.as_tensor(rows, device=xd.device)
+                out[:, sel_rows] = self.forward_multi_k(tt[rows], xd[sel_rows], kernelsizes, label=lab_g, device=device)
+            return out
+        beta_cpu = self.schedule(tt.cpu().float())
+        beta = beta_cpu.to(eng.device, torch.float32).contiguous()
+        beta_min = float(beta_cpu.min())
+        lab = _as_label(label)
+        sel = self.selection(lab)
+        for q, k in enumerate(kernelsizes):
+            k = int(k)
+            sel_ls = self.selection(lab, kind="LS") if (self.kind == "bbELS" and k >= xd.shape[-2]) else None
+            eng.evaluate(self.kind, xd, beta, k, sel, query_pad=self.query_pad, mu=None, score=out[q], beta_min=beta_min,
+                         sel_ls=sel_ls)
+        return out
 
 
 class LocalScoreModule(_ScoreModuleBase):

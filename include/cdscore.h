@@ -117,6 +117,17 @@ int cds_els_umma_pv_supported(int C, int H, int W, int k, int passes, int bank_p
 /* dynamic shared memory the umma kernel needs for this geometry (0 = unsupported geometry) */
 int64_t cds_els_umma_smem_bytes(int C, int H, int W, int k, int passes, int bank_planes);
 
+/* Vector-Jacobian product of the denoised estimate: grad_mu[b][c'][y][x'] += sum over query pixels (i,j) and channels c of
+ * g[b][c][i][j] * d mu[b][c][i][j] / d x[b][c'][y][x'], exact fp32 SIMT in the unified form of cds_partials_simt (same kind /
+ * query_pad / idx / logw).  m, l [B][H*W] and mu [B][C][H*W] are the MERGED results of a cds_partials_simt evaluation of the same
+ * inputs (m in log2 units including the |q|^2 term, i.e. not those of the tensor-core kernel).  The reference's callers
+ * obtain this product by autograd through the Python modules (src/utils/exterior_derivative.py:68-79); here it is closed form:
+ * d mu_c / d q_e = (a/beta) sum_p w_p (v_p[c] - mu_c) p_e.  grad_mu must be zeroed by the caller (atomic adds; slices of the
+ * bank -- CTA splits, ranks -- simply accumulate).  The score's gradient is  -g/beta + (a/beta) grad_mu. */
+int cds_score_vjp_simt(int kind, int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
+                       const float* images, const int32_t* idx, const float* logw, int64_t n_sel, int splits,
+                       const float* m, const float* l, const float* mu, const float* g, float* grad_mu, void* stream);
+
 /* ---- merge + epilogue */
 
 /* log-sum-exp merge of S slices into slice 0 of (m_out,l_out,acc_out) (may alias the inputs) */

@@ -226,6 +226,28 @@ def ddpm_cases(ref):
     return cases
 
 
+def grad_cases(ref):
+    """Vector-Jacobian products of the score obtained by autograd THROUGH the reference modules (what the reference's
+    exterior-derivative callers do, src/utils/exterior_derivative.py:68-79): grad = d/dx sum(score(x) * g)."""
+    cases = []
+    for kind, c, h, n, k, t, label, bs, seed in [("ELS", 3, 8, 12, 3, 0.4, None, 8, 41), ("ELS", 1, 12, 10, 5, 0.7, 1, 4, 42),
+                                                 ("bbELS", 3, 10, 10, 3, 0.5, None, 10, 43), ("bbELS", 1, 12, 12, 5, 0.3, None, 6, 44),
+                                                 ("LS", 3, 10, 16, 3, 0.6, None, 16, 45), ("IS", 1, 8, 12, 3, 0.5, None, 12, 46)]:
+        bank, labels = synthetic_bank(n, c, h, nlabels=3, seed=seed)
+        mod = _module(ref, kind, ref_loader.TensorBank(bank, labels), k, bs, None)
+        gen = torch.Generator().manual_seed(500 + seed)
+        x = torch.randn(1, c, h, h, generator=gen).requires_grad_(True)
+        g = torch.randn(1, c, h, h, generator=gen)
+        lab = None if label is None else torch.tensor([label])
+        s = mod(torch.tensor([t]), x, label=lab, device=torch.device("cpu"))
+        (grad,) = torch.autograd.grad((s * g).sum(), x)
+        cases.append(dict(kind=kind, bank=bank.numpy(), labels=labels.numpy(), x=x.detach().numpy(), g=g.numpy(), t=np.float64(t),
+                          k=np.int64(k), label=np.int64(-1 if label is None else label), batch_size=np.int64(bs),
+                          score=s.detach().numpy(), grad=grad.numpy()))
+        print(f"grad {kind} C={c} H={h} N={n} k={k}: |grad|max={grad.abs().max():.3f}")
+    return cases
+
+
 def schedule_cases(ref):
     t = torch.arange(0, 21, dtype=torch.float32) / 20
     return dict(t=t.numpy(), cosine=ref.cosine_noise_schedule(t).numpy(),
@@ -258,6 +280,8 @@ def main():
         save(f"machine_{i:02d}_{c['kind']}.npz", c)
     for i, c in enumerate(machinex_cases(ref)):
         save(f"machinex_{i:02d}_{c['kind']}.npz", c)
+    for i, c in enumerate(grad_cases(ref)):
+        save(f"grad_{i:02d}_{c['kind']}.npz", c)
     for i, c in enumerate(ddpm_cases(ref)):
         save(f"ddpm_{i:02d}_{c['kind']}.npz", c)
     save("schedule.npz", schedule_cases(ref))

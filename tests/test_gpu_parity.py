@@ -168,6 +168,36 @@ def test_ddpm_device_noise_stream():
     assert not torch.allclose(ddim, outs[True][0])
 
 
+@pytest.mark.parametrize("path", golden_files("grad"), ids=os.path.basename)
+def test_score_gradient_golden(path):
+    """Differentiable score modules: autograd through the CUDA module (closed-form backward, cds_score_vjp_simt) against
+    the vector-Jacobian product autograd takes through the reference's Python module (what src/utils/exterior_derivative.py
+    does), for ELS / bbELS / LS / IS incl. a label filter and the per-batch mean quirk."""
+    c = load_case(path)
+    kind = str(c["kind"])
+    label = None if int(c["label"]) < 0 else int(c["label"])
+    k = int(c["k"])
+    mod = _make(kind, _dataset(c["bank"], c["labels"]), k, int(c["batch_size"]), None)
+    x = torch.from_numpy(c["x"]).cuda().requires_grad_(True)
+    g = torch.from_numpy(c["g"]).cuda()
+    lab = None if label is None else torch.tensor([label])
+    s = mod(torch.tensor([float(c["t"])]), x, label=lab, device=torch.device("cuda"))
+    assert s.requires_grad
+    (grad,) = torch.autograd.grad((s * g).sum(), x)
+    ref_s, ref_g = c["score"].astype(np.float64), c["grad"].astype(np.float64)
+    assert np.max(np.abs(s.detach().cpu().double().numpy() - ref_s)) < 2e-3 * max(1.0, np.max(np.abs(ref_s)))
+    err = np.max(np.abs(grad.cpu().double().numpy() - ref_g))
+    assert err < 2e-3 * max(1.0, np.max(np.abs(ref_g))), (err, np.max(np.abs(ref_g)))
+    # the full Jacobian through torch.autograd.functional.jacobian, as ExteriorDerivative.forward does, on a few rows
+    if c["x"].size <= 200:
+        from torch.autograd.functional import jacobian
+        t = torch.tensor([float(c["t"])])
+        f = lambda xf: mod(t, xf.view(1, *c["x"].shape[1:]), label=lab, device=torch.device("cuda")).view(-1)
+        jac = jacobian(f, x.detach().view(-1))
+        assert jac.shape == (c["x"].size, c["x"].size)
+        assert torch.allclose(jac.t() @ g.view(-1), grad.view(-1), atol=2e-3 * max(1.0, float(np.max(np.abs(ref_g)))))
+
+
 def test_full_bank_parity_at_benchmarked_size(cifar_bank):
     """The headline configuration itself (50 000-image bank, one class = 5 063 images, the shipped CIFAR schedule, x taken
     from a real trajectory): at the steps i = 1 (k=3, two query passes, lowest noise), 7 (k=7, two passes, just above the
@@ -478,7 +508,7 @@ def test_calibration_recovers_the_kernel_size_of_an_analytic_model():
     teacher = cd.LocalEquivScoreModule((bank, labels), kernel_size=7, batch_size=8, schedule=cd.cosine_noise_schedule)
 
     def model(t, x, label=None):
-        beta = cd.cosine_noise_schedule(t.cpu()).to(x.device)
+        beta = cd.cosine_noise_schedule(t.cpu()).to(x.device)[:, None, None, None]
         return -teacher(t, x, label=label, device=x.device) * beta ** 0.5
 
     out = calibrate(model, (bank, labels), kernelsizes=[3, 5, 7, 9], scoremoduletype="ELS", scorebatchsize=8, nsamps=2,
@@ -487,6 +517,39 @@ def test_calibration_recovers_the_kernel_size_of_an_analytic_model():
     # the last column is t = 1 (beta = 0.9998, a = 0.012): the score is -x to 1e-6 for every kernel size, so the
     # argmax there is decided by rounding noise, in the reference as well
     assert torch.all(out["median"][:-1] == 7) and torch.all(out["mode"][:-1] == 7)
+
+
+def test_calibration_batched_equals_serial():
+    """All calibration trajectories advanced together (every bank pass shared by the samples, the candidate sizes of a step
+    evaluated back to back by forward_multi_k) pick exactly the kernel sizes of the sample-by-sample loop of the reference
+    (scripts/scales_calibration.py:128-178), for a conditional run with per-sample labels."""
+    from convolutional_diffusion_b200.scales_calibration import calibrate
+    from convolutional_diffusion_b200.synthetic import synthetic_bank
+    cd = _mods()
+    bank, labels = synthetic_bank(96, 3, 16, nlabels=3, seed=6)
+    teacher = cd.LocalEquivBordersScoreModule((bank, labels), kernel_size=5, batch_size=8, schedule=cd.cosine_noise_schedule)
+
+    def model(t, x, label=None):          # a stand-in denoiser: the bbELS score of size 5 plus a smooth perturbation
+        beta = cd.cosine_noise_schedule(t.cpu()).to(x.device)[:, None, None, None]
+        return -(teacher(t, x, label=label, device=x.device) + 0.05 * torch.tanh(x)) * beta ** 0.5
+
+    outs = []
+    for sb in (None, 1, 2):
+        outs.append(calibrate(model, (bank, labels), kernelsizes=[3, 5, 7], scoremoduletype="bbELS", conditional=True,
+                              nlabels=3, scorebatchsize=8, nsamps=4, nsteps=4, generator=torch.Generator().manual_seed(3),
+                              samplebatch=sb))
+    # (the last column is t = 1, where every size gives the score -x to 1e-6 and rounding noise picks the arg max)
+    assert torch.equal(outs[0]["k_optimals"][:, :-1], outs[1]["k_optimals"][:, :-1])
+    assert torch.equal(outs[0]["k_optimals"][:, :-1], outs[2]["k_optimals"][:, :-1])
+    assert torch.all(outs[0]["median"][:-1] == 5)
+    # forward_multi_k == one call per size
+    mod = cd.LocalEquivScoreModule((bank, labels), kernel_size=3, batch_size=8, schedule=cd.cosine_noise_schedule)
+    x = torch.randn(3, 3, 16, 16, generator=torch.Generator().manual_seed(1)).cuda()
+    t = torch.tensor([0.3, 0.5, 0.7])
+    lab = torch.tensor([0, 2, 0])
+    multi = mod.forward_multi_k(t, x, [3, 5, 9], label=lab, device="cuda")
+    for q, k in enumerate([3, 5, 9]):
+        assert torch.equal(multi[q], mod(t, x, label=lab, device="cuda", k=k))
 
 
 @pytest.mark.parametrize("k,t", [(3, 0.15), (9, 0.55), (17, 0.9)])
