@@ -239,6 +239,7 @@ def run_ours(args, w):
     B, C, H, NL = args.batch, w["C"], w["H"], w["nlabels"]
     replica = world > 1 and args.shard == "replica"
     scales, evals = schedule_of(w)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))      # torchrun pins OMP to 1 thread: bank synthesis
     bank, labels = synthetic_bank(w["N"], C, H, nlabels=NL, seed=0)
     group = dist.group.WORLD if (world > 1 and not replica) else None
     cls = {"ELS": cd.LocalEquivScoreModule, "bbELS": cd.LocalEquivBordersScoreModule, "LS": cd.LocalScoreModule}[w["kind"]]
@@ -400,9 +401,10 @@ def roofline(w, args, cd, mod, machine, eng, evals, scales, x0, dev, peaks, B):
         else:
             mu = torch.empty_like(x)
             fn = lambda: eng.evaluate("bbELS", x, beta, k, sel, mu=mu, beta_min=beta_val)
-        for _ in range(2):
+        heavy = w["mode"] == "sweep"                          # a 64x64 evaluation takes seconds: one warm-up, one timed launch
+        for _ in range(1 if heavy else 2):
             fn()
-        reps = 3
+        reps = 1 if heavy else 3
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         a.record()
@@ -463,6 +465,7 @@ def main():
     ap.add_argument("--workload", default="els_cifar10_conditional", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--shard", default="bank", choices=["bank", "replica"])
+    ap.add_argument("--bank", type=int, default=None, help="bank size override (smoke runs; the named size is the default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "f16x2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -471,7 +474,10 @@ def main():
     w = dict(WORKLOADS[args.workload], name=args.workload)
     if args.batch is None:
         args.batch = w["batch"]
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.bank is not None:
+        w["N"] = args.bank
+    if args.impl == "ours" and w["mode"] != "sweep":
+        args.warmup = max(args.warmup, 3)                     # (the 64x64 sweep takes seconds per step: --warmup is honoured)
     if args.impl == "reference":
         run_reference(args, w)
     else:
