@@ -38,7 +38,7 @@
 //     operand.  V' (centre pixels and a ones row, fp16, exact for 8-bit banks) is routed per chunk to the 4 O columns of
 //     the epilogue warpgroup that owns the chunk, so every (warpgroup, row) has a private reference m_ref and a private
 //     accumulator and nothing is exchanged per tile.  m_ref is not a running max: it is re-based on a fixed schedule
-//     (before image 1, 2, 4, 8, ... of the CTA's slice: drain O into the thread's fp32 state, m_ref = best logit seen);
+//     (before tile 1, 2, 4, 8, ... of the CTA's slice: drain O into the thread's fp32 state, m_ref = best logit seen);
 //     a chunk holding a logit more than 2^7.5 above m_ref (fp16 overflow) is evaluated exactly on the CUDA cores into the
 //     same fp32 state and stores P = 0, so the result never depends on how good the reference is -- only the speed does.
 //     Measured basis (profiles/r02_tmem_ld_floor.log): tcgen05.ld 32x32b delivers 700-800 B/clk/SM (the 16x256b shape
@@ -561,20 +561,23 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
       int unit = 0;
       for (int n = 0; n < n_img; ++n) {
         const float lw = __ldg(p.logw + n0 + n) * CDS_LOG2E;
-        if (n > 0 && (n & (n - 1)) == 0 && T + 1u < total_tiles) {      // re-base the reference before image 1, 2, 4, 8, ...
-          if (o_dirty) {
-            drain(T);
-#ifdef CDS_PROFILE_SWITCHES
-            ++cnt_drain;
-#endif
-          }
-          m_ref = m_seen;
-        }
-        const float off = lw - m_ref + PV_SHIFT;           // +inf while there is no reference yet (then every chunk is exact)
-        const float2 off2 = make_float2(off, off);
         for (int ch = 0; ch < g.nchunks; ++ch, ++unit) {
           const int s = unit & 1;
           for (int vb = 0; vb < nvb; ++vb, ++T) {
+            // re-base the reference before tile 1, 2, 4, 8, ... of the CTA's slice (tiles, not images: only the very first
+            // tile runs without a reference, i.e. on the exact path -- a whole image would cost several per cent of a CTA
+            // that owns ~70 images when the bank is sharded over 8 GPUs)
+            if (T > 0u && (T & (T - 1u)) == 0u && T + 1u < total_tiles) {
+              if (o_dirty) {
+                drain(T);
+#ifdef CDS_PROFILE_SWITCHES
+                ++cnt_drain;
+#endif
+              }
+              m_ref = m_seen;
+            }
+            const float off = lw - m_ref + PV_SHIFT;       // +inf while there is no reference yet (then every unit is exact)
+            const float2 off2 = make_float2(off, off);
             const uint32_t buf = T & 1u;
 #ifdef CDS_PROFILE_SWITCHES
             const long long ek0 = clock64();
