@@ -112,9 +112,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug must become a trap (CUDA error), never a hung GPU
+// bounded wait: a protocol bug must become a trap (CUDA error), never a hung GPU.  2^30 polls: a try_wait that fails
+// suspends the thread for a hardware-chosen slice first, so this is minutes of wall clock -- far beyond any healthy wait,
+// also under a profiler or time-slicing (round 1 trapped after 2^22 polls, which ncu replays could reach).  A time-based
+// bound (%globaltimer) was tried and dropped: inline it costs the FMA epilogue registers (spills 16 -> 28 bytes), out of
+// line the call spills more.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  for (uint32_t it = 0; it < (1u << 22); ++it)
+  for (uint32_t it = 0; it < (1u << 30); ++it)
     if (mbar_try(bar, parity)) return;
   printf("cdscore: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
          threadIdx.x);

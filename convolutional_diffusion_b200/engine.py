@@ -199,6 +199,11 @@ class ScoreEngine:
         variant = _lib.ELS_VARIANT[self.els_variant]
         if variant == 2 and (dbg is not None or not self.lib.cds_els_umma_pv_supported(b.C, b.H, b.W, k, passes, planes)):
             variant = 1                                            # "pv" means: wherever the geometry allows it
+        if variant == 0 and n_sel < 400 * S:
+            # the P.V epilogue has a start-up cost per CTA (the first tile runs on the exact path, ~11 re-basings of the
+            # reference): with fewer than ~400 images per CTA -- small banks, or the headline bank sharded over 4-8 GPUs --
+            # the FMA epilogue is faster (6 250-image bank, 70 images per CTA: 18.8 vs 20.7 ms per step)
+            variant = 1
         if variant == 0 and a_over_beta is not None and a_over_beta > 100.0:
             # at the lowest noise levels most 16-column chunks carry no weight at all (77 % at a/beta = 165 on the headline
             # trajectory): the FMA-pipe epilogue skips them outright, the P.V epilogue still stores and contracts zeros
