@@ -84,6 +84,22 @@ def pairs_per_eval(kind, H, k, n):
     return n * (i ** 4 + 4 * d * i * i + 4 * d * d)
 
 
+def flops_per_eval(kind, H, k, C, n):
+    """Algorithmic FLOP of one evaluation of one sample: 2 per patch element and pair.  ELS pairs contract whole k*k*C
+    patches; LS (and bbELS corners) a window clipped by the border; a bbELS edge pair at depth r the (r+d+1) x k rows of the
+    truncated patch."""
+    d = k // 2
+    if kind == "ELS":
+        return pairs_per_eval(kind, H, k, n) * 2 * k * k * C
+    clip = [min(H - 1, y + d) - max(0, y - d) + 1 for y in range(H)]           # window extent per coordinate
+    if kind == "LS" or (kind == "bbELS" and k >= H):
+        return n * 2 * C * sum(clip) ** 2
+    i = H - 2 * d
+    edge = sum(r + d + 1 for r in range(d)) * k                                # patch elements per channel, summed over depths
+    corner = sum(r + d + 1 for r in range(d)) ** 2
+    return n * 2 * C * (i ** 4 * k * k + 4 * i * i * edge + 4 * corner)
+
+
 def schedule_of(w):
     """[(i, k, t)] of the evaluations of one step of a workload."""
     from convolutional_diffusion_b200.scales import load_scales
@@ -101,7 +117,7 @@ def step_pairs_flops(w, evals, n_c):
     for _, k, _ in evals:
         p = pairs_per_eval(w["kind"], w["H"], k, n_c)
         pairs += p
-        flops += p * 2 * k * k * w["C"]
+        flops += flops_per_eval(w["kind"], w["H"], k, w["C"], n_c)
     return pairs, flops
 
 
@@ -420,7 +436,7 @@ def roofline(w, args, cd, mod, machine, eng, evals, scales, x0, dev, peaks, B):
         count = len(per_eval[k])
         ms = sum(per_eval[k]) / count
         p = B * pairs_per_eval(w["kind"], w["H"], k, n_c)
-        fl = p * 2 * k * k * w["C"]
+        fl = B * flops_per_eval(w["kind"], w["H"], k, w["C"], n_c)
         per_k[str(k)] = {"ms": round(ms, 4), "pairs_per_s": p / ms * 1e3, "tflops": fl / ms * 1e-9, "evals": count}
         tot_ms += ms * count
         tot_fl += fl * count
@@ -432,13 +448,13 @@ def roofline(w, args, cd, mod, machine, eng, evals, scales, x0, dev, peaks, B):
                 "note": f"algorithmic bytes = selected images x C*H*W x {eng.bank.ls_bytes_per_pixel()} B (the bank streamed once per "
                         f"evaluation for all {B} samples) / CUDA-event kernel time", "per_k": per_k}
     achieved = tot_fl / tot_ms * 1e-9
-    out = {"bound": "tensor", "kernel": "els_umma_kernel" if w["kind"] == "ELS" else "bbELS: els_umma_kernel (centre) + bbels_edge + ls (corners)",
+    out = {"bound": "tensor", "kernel": "els_umma_kernel" if w["kind"] == "ELS" else "bbELS: els_umma_kernel (centre window) + bbels_edge_umma_kernel (edge bands) + ls_rows_kernel (corners)",
            "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
            "frac_sustained": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"],
            "traffic": 712.0e6 if w["name"] == "els_cifar10_conditional" else None,
            "traffic_source": "ncu --set full capture of round 1 at batch 4, class 0, k=17 (profiles/r01g_els_umma_ncu_summary.md), "
                              "not re-measured by this run" if w["name"] == "els_cifar10_conditional" else None,
-           "note": "algorithmic 2*k*k*C FLOP per (query, patch) pair, FLOP-weighted over the evaluations of one step, each on the "
+           "note": "algorithmic 2 FLOP per patch element and (query, patch) pair (2*k*k*C for ELS; truncated patches counted as such for bbELS edges/corners), FLOP-weighted over the evaluations of one step, each on the "
                    "x of its own step; CUDA events around the launches on the launching stream", "per_k": per_k}
     if w["name"] == "bbels_cifar10_k17":                     # the ELS / circular counterpart of configs[3]
         k, t = w["k"], w["t"]

@@ -34,8 +34,16 @@ SIGNATURES = {
     "cds_ls_rows_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_bbels_edge_supported": (_i, [_i, _i, _i, _i]),
     "cds_bbels_edge_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "cds_bbels_edge_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "cds_edge_plane_halves": (_i64, [_i64, _i, _i]),
+    "cds_edge_norms_halves": (_i64, [_i64, _i, _i]),
+    "cds_pack_edge_plane": (_i, [_p, _i64, _i, _i, _f, _p, _p]),
+    "cds_pack_edge_norms": (_i, [_p, _i64, _i, _i, _i, _p, _p]),
+    "cds_bbels_edge_partials_umma": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
     "cds_els_partials_umma": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _i,
                                    _p, _p, _p, _p, _p]),
+    "cds_els_partials_umma_window": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _i,
+                                          _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "cds_els_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
     "cds_els_umma_pv_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "cds_combine": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -82,6 +82,8 @@ class PatchBank:
         self._rows8 = None
         self._pnorm = {}
         self._nplane = {}
+        self._eplane = None
+        self._enorms = {}
         self._sel = {}
 
     # ---- layouts -------------------------------------------------------------------------------
@@ -138,6 +140,32 @@ class PatchBank:
                                                         _lib.ptr(out), _lib.stream_ptr()), "cds_pack_norm_plane")
                 self._nplane[k] = out
         return self._nplane[k]
+
+    def edge_plane(self):
+        """fp16 plane of the four border bands in one orientation (8-pixel granules ACROSS the band, k independent) for the
+        tensor-core bbELS edge kernel; same scale as strip8.  None for a two-plane bank."""
+        hi, lo, scale = self.strip8()
+        if lo is not None:
+            return None
+        if self._eplane is None:
+            with torch.cuda.device(self.device):
+                n = int(self.lib.cds_edge_plane_halves(self.N_local, self.C, self.H))
+                out = torch.empty(n, dtype=torch.float16, device=self.device)
+                _lib.check(self.lib.cds_pack_edge_plane(_lib.ptr(self.images), self.N_local, self.C, self.H, scale,
+                                                        _lib.ptr(out), _lib.stream_ptr()), "cds_pack_edge_plane")
+                self._eplane = out
+        return self._eplane
+
+    def edge_norms(self, k):
+        """fp16 squared norms of the truncated border patches of kernel size k as K granules (computed once per k)."""
+        if k not in self._enorms:
+            with torch.cuda.device(self.device):
+                n = int(self.lib.cds_edge_norms_halves(self.N_local, self.H, k))
+                out = torch.empty(n, dtype=torch.float16, device=self.device)
+                _lib.check(self.lib.cds_pack_edge_norms(_lib.ptr(self.images), self.N_local, self.C, self.H, k,
+                                                        _lib.ptr(out), _lib.stream_ptr()), "cds_pack_edge_norms")
+                self._enorms[k] = out
+        return self._enorms[k]
 
     def ls_bytes_per_pixel(self):
         """Bytes per bank pixel the LS kernels stream from HBM (algorithmic bytes of the roofline)."""

@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(THREADS, 1) els_umma_kernel(const __grid_const
 #else
   constexpr int W_PROD = 0, W_MMA = 1, W_B0 = 2, W_EPI0 = 4;     // A/B: the round-1 assignment
 #endif
-  const int tiles_j = (g.W + TJ - 1) / TJ;
-  const int i0 = (blockIdx.x / tiles_j) * TI, j0 = (blockIdx.x % tiles_j) * TJ;
+  // query window: the tiles cover the pixels [qi0, qi0+qrows) x [qj0, qj0+qcols) (the whole image, or the bbELS centre)
+  const int tiles_j = (p.qcols + TJ - 1) / TJ;
+  const int i0 = p.qi0 + (blockIdx.x / tiles_j) * TI, j0 = p.qj0 + (blockIdx.x % tiles_j) * TJ;
   const int split = blockIdx.y, b = blockIdx.z;
   const long long n0 = p.n_sel * split / p.splits, n1 = p.n_sel * (split + 1) / p.splits;
   const int n_img = (int)(n1 - n0);
@@ -1105,12 +1106,16 @@ bool pick_geom(int C, int H, int W, int k, int passes, int planes, int pv, bool 
 }
 }  // namespace
 
-extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
-                                     const void* bank_hi, const void* bank_lo, const void* bank_rows, float bank_scale,
-                                     const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
-                                     int splits, int passes, int variant, float* m, float* l, float* acc, float* dbg_dots,
-                                     void* stream) {
+extern "C" int cds_els_partials_umma_window(int query_pad, const float* x, int B, int C, int H, int W, int k,
+                                            const float* beta, const void* bank_hi, const void* bank_lo,
+                                            const void* bank_rows, float bank_scale, const void* norm_plane,
+                                            const int32_t* idx, const float* logw, int64_t n_sel, int splits, int passes,
+                                            int variant, int qi0, int qj0, int qrows, int qcols, float* m, float* l,
+                                            float* acc, float* dbg_dots, void* stream) {
   UmmaParams p;
+  CDS_CHECK_ARG(qi0 >= 0 && qj0 >= 0 && qrows >= 1 && qcols >= 1 && qi0 + qrows <= H && qj0 + qcols <= W,
+                "cds_els_partials_umma_window: window (%d,%d)+(%d,%d) outside the %dx%d image", qi0, qj0, qrows, qcols, H, W);
+  p.qi0 = qi0; p.qj0 = qj0; p.qrows = qrows; p.qcols = qcols;
   const int planes = bank_lo ? 2 : 1;
   const char* mx = getenv("CDS_ELS_MIXED");     // A/B switch: 0 = vertical granules only
   const bool try_mixed = bank_rows != nullptr && !(mx && atoi(mx) == 0);
@@ -1154,7 +1159,7 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
     const char* at = getenv("CDS_A_TMEM");     // A/B switch: 0 = every query slice from shared memory
     if (at && atoi(at) == 0) p.g.n_tmem = p.g.n_h;   // the horizontal slices of the mixed layout exist only in TMEM
   }
-  const int tiles = ((H + TI - 1) / TI) * ((W + TJ - 1) / TJ);
+  const int tiles = ((qrows + TI - 1) / TI) * ((qcols + TJ - 1) / TJ);
   dim3 grid(tiles, splits, B);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
@@ -1178,4 +1183,13 @@ extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C
   }
   CDS_CHECK_LAUNCH("els_umma_kernel");
   return CDS_OK;
+}
+
+extern "C" int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, int W, int k, const float* beta,
+                                     const void* bank_hi, const void* bank_lo, const void* bank_rows, float bank_scale,
+                                     const void* norm_plane, const int32_t* idx, const float* logw, int64_t n_sel,
+                                     int splits, int passes, int variant, float* m, float* l, float* acc, float* dbg_dots,
+                                     void* stream) {
+  return cds_els_partials_umma_window(query_pad, x, B, C, H, W, k, beta, bank_hi, bank_lo, bank_rows, bank_scale, norm_plane,
+                                      idx, logw, n_sel, splits, passes, variant, 0, 0, H, W, m, l, acc, dbg_dots, stream);
 }

@@ -73,6 +73,7 @@ struct UmmaGeom {
 struct UmmaParams {
   UmmaGeom g;
   int B, pad, splits;
+  int qi0, qj0, qrows, qcols;   // query window in pixels: the whole image, or the bbELS centre region
   long long n_sel;
   const float* x;
   const float* beta;

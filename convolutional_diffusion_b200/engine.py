@@ -50,6 +50,8 @@ class ScoreEngine:
         # epilogue of the ELS tensor-core kernel: "auto" (P.V contraction on the tensor cores where supported and measured
         # faster: k <= 9 and a/beta <= 100), "fma" (weighted sum on the FMA pipe), "pv" (P.V wherever supported); CDS_ELS_VARIANT overrides
         self.els_variant = os.environ.get("CDS_ELS_VARIANT", "auto")
+        self.centre_window = os.environ.get("CDS_CENTRE_WINDOW", "1") != "0"   # A/B switch: 0 = centre kernel over all pixels
+        self.edge_variant = os.environ.get("CDS_EDGE_VARIANT", "auto")       # "simt": keep the bbELS edge bands off the tensor cores
         if self.els_variant not in _lib.ELS_VARIANT:
             raise ValueError(f"CDS_ELS_VARIANT must be one of {sorted(_lib.ELS_VARIANT)}, got {self.els_variant!r}")
         self._buf = {}
@@ -169,13 +171,31 @@ class ScoreEngine:
         b = self.bank
         return self.use_tensor_cores and bool(self.lib.cds_bbels_edge_supported(b.C, b.H, b.W, k))
 
-    def edge_partials(self, x, beta, k, sel, tag="edge"):
-        """bbELS edge bands (csrc/bbels_edge.cu); writes the edge pixels of the partials only."""
+    def edge_umma_supported(self, k, passes):
+        """Tensor-core edge bands: single exact bank plane, square images, a geometry that fits shared memory."""
+        b = self.bank
+        return (self.use_tensor_cores and self.edge_variant != "simt" and b.H == b.W
+                and b.strip8()[1] is None and self.lib.cds_bbels_edge_umma_smem_bytes(b.C, b.H, b.W, k, passes) > 0)
+
+    def edge_partials(self, x, beta, k, sel, tag="edge", passes=2):
+        """bbELS edge bands: csrc/bbels_edge_umma.cu (tcgen05, `passes` as for the centre) where the geometry fits, else the
+        exact fp32 SIMT kernel csrc/bbels_edge.cu; writes the edge pixels of the partials only."""
         idx, logw, n_sel = sel
         if n_sel == 0:
             return self._empty_shard(tag, x.shape[0])
         b = self.bank
         B = x.shape[0]
+        if self.edge_umma_supported(k, passes):
+            d = k // 2
+            mt = (((b.H - 2 * d + 7) // 8) * d + 15) // 16           # M tiles per band (bbels_edge_umma.cu: EdgeGeom::MT)
+            S = self._splits(4 * mt, B, n_sel, waves=1, min_images=32)
+            P = self._partials(tag, S, B)
+            _lib.check(self.lib.cds_bbels_edge_partials_umma(
+                _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(b.edge_plane()), b.strip8()[2],
+                _lib.ptr(b.edge_norms(k)), _lib.ptr(idx), _lib.ptr(logw), n_sel, S, passes, _lib.ptr(P.m), _lib.ptr(P.l),
+                _lib.ptr(P.acc), _lib.stream_ptr()), "cds_bbels_edge_partials_umma")
+            self.launches += 1
+            return P
         S = int(max(1, min(n_sel // 8, (4 * sm_count(self.device)) // (4 * B))))
         P = self._partials(tag, S, B)
         _lib.check(self.lib.cds_bbels_edge_partials(_lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(b.images),
@@ -184,7 +204,8 @@ class ScoreEngine:
         self.launches += 1
         return P
 
-    def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma", a_over_beta=None):
+    def umma_partials(self, pad, x, beta, k, sel, passes, dbg=None, tag="umma", a_over_beta=None, window=None):
+        """window = (i0, j0, rows, cols): only the query tiles covering that pixel window are launched (bbELS centre)."""
         idx, logw, n_sel = sel
         if n_sel == 0:
             return self._empty_shard(tag, x.shape[0])
@@ -192,7 +213,8 @@ class ScoreEngine:
         B = x.shape[0]
         hi, lo, scale = b.strip8()
         pn = b.norm_plane(k)
-        tiles = ((b.H + 15) // 16) * ((b.W + 7) // 8)
+        qi0, qj0, qrows, qcols = window if window is not None else (0, 0, b.H, b.W)
+        tiles = ((qrows + 15) // 16) * ((qcols + 7) // 8)
         S = self._splits(tiles, B, n_sel)
         P = self._partials(tag, S, B)
         planes = 1 if lo is None else 2
@@ -209,10 +231,10 @@ class ScoreEngine:
             # trajectory): the FMA-pipe epilogue skips them outright, the P.V epilogue still stores and contracts zeros
             variant = 1
         rows = b.rows8() if (k > 8 and k % 8) else None            # mixed K layout for the trailing k % 8 patch rows
-        _lib.check(self.lib.cds_els_partials_umma(
+        _lib.check(self.lib.cds_els_partials_umma_window(
             _lib.PAD[pad], _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(rows),
-            scale, _lib.ptr(pn), _lib.ptr(idx), _lib.ptr(logw), n_sel, S, passes, variant, _lib.ptr(P.m), _lib.ptr(P.l),
-            _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr()), "cds_els_partials_umma")
+            scale, _lib.ptr(pn), _lib.ptr(idx), _lib.ptr(logw), n_sel, S, passes, variant, qi0, qj0, qrows, qcols,
+            _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc), _lib.ptr(dbg), _lib.stream_ptr()), "cds_els_partials_umma_window")
         self.launches += 1
         return P
 
@@ -307,10 +329,14 @@ class ScoreEngine:
             # every partials kernel reads x, so all of them run before the first finish (which may advance x in place);
             # the regions are disjoint sets of pixels, each finish touches only its own
             if self.umma_supported(k, passes):
-                Pc = self.umma_partials("zeros", x, beta, k, sel, passes, a_over_beta=self._a_over_beta(beta_min))
-                if self.edge_supported(k) and self.ls_supported(k):
+                has_edges = (self.edge_umma_supported(k, passes) or self.edge_supported(k)) and self.ls_supported(k)
+                # only the centre pixels of this kernel's output are used: launch just the query tiles that cover them
+                window = (d, d, b.H - 2 * d, b.W - 2 * d) if self.centre_window else None
+                Pc = self.umma_partials("zeros", x, beta, k, sel, passes, a_over_beta=self._a_over_beta(beta_min),
+                                        window=window)
+                if has_edges:
                     # edge bands: dedicated kernel; corners see only their own location = the LS kernel
-                    Pe = self.edge_partials(x, beta, k, sel)
+                    Pe = self.edge_partials(x, beta, k, sel, passes=passes)
                     Pk = self.ls_partials(x, beta, k, sel, tag="corner")
                     self.finish(Pc, x, beta, mu, score, region=1, d=d, step=step)
                     self.finish(Pe, x, beta, mu, score, region=4, d=d, step=step)

@@ -92,6 +92,24 @@ int cds_bbels_edge_partials(const float* x, int B, int C, int H, int W, int k, c
                             const int32_t* idx, const float* logw, int64_t n_sel, int splits, float* m, float* l,
                             float* acc, void* stream);
 
+/* The same edge bands on the tensor cores (tcgen05, csrc/bbels_edge_umma.cu): per band ONE contraction with all depths
+ * stacked on the query side -- the depth truncation of a patch is a zeroing of query rows, the candidate operand (the k-1
+ * image rows under the border as 8-pixel granules across the band) is depth independent.  passes as in
+ * cds_els_partials_umma (1 = fp16 query, 2 = fp16 hi + lo); the bank must be one exact fp16 plane (same `scale` as
+ * cds_pack_strip8), otherwise use cds_bbels_edge_partials.  Bank side, packed once: cds_pack_edge_plane (k independent,
+ * cds_edge_plane_halves fp16 values: [n][band][c][ceil(H/8)][H] granules of 8 pixels across the band) and
+ * cds_pack_edge_norms (per k, cds_edge_norms_halves values: squared norms of the truncated patches as K granules).
+ * cds_bbels_edge_umma_smem_bytes = 0: geometry not supported.  Writes the partials of the edge pixels only. */
+int64_t cds_bbels_edge_umma_smem_bytes(int C, int H, int W, int k, int passes);
+int64_t cds_edge_plane_halves(int64_t N, int C, int H);
+int64_t cds_edge_norms_halves(int64_t N, int H, int k);
+int cds_pack_edge_plane(const float* images, int64_t N, int C, int H, float scale, void* out_f16, void* stream);
+int cds_pack_edge_norms(const float* images, int64_t N, int C, int H, int k, void* out_f16, void* stream);
+int cds_bbels_edge_partials_umma(const float* x, int B, int C, int H, int W, int k, const float* beta,
+                                 const void* edge_plane, float scale, const void* edge_norms, const int32_t* idx,
+                                 const float* logw, int64_t n_sel, int splits, int passes, float* m, float* l,
+                                 float* acc, void* stream);
+
 /* tcgen05 / TMEM evaluation of ELS (and the bbELS centre region): queries = all H*W pixels of x padded
  * per query_pad, candidates = every valid k x k patch of the selected images, streamed from the strip8
  * bank by bulk-async copies.  passes = 1: fp16 query; 2: fp16 hi+lo query (fp32-grade dot products for
@@ -112,6 +130,14 @@ int cds_els_partials_umma(int query_pad, const float* x, int B, int C, int H, in
                           float bank_scale, const void* norm_plane, const int32_t* idx, const float* logw,
                           int64_t n_sel, int splits, int passes, int variant, float* m, float* l, float* acc,
                           float* dbg_dots, void* stream);
+/* The same restricted to the query window [qi0, qi0+qrows) x [qj0, qj0+qcols) of x: only the 128-pixel query tiles that
+ * cover the window are launched (the bbELS centre region, idealscore.py:218-254, is the window (d,d)+(H-2d, W-2d): 2 tiles
+ * instead of 8 for k = 17 on 32x32).  Pixels outside the window are not written, except those that share a tile with it. */
+int cds_els_partials_umma_window(int query_pad, const float* x, int B, int C, int H, int W, int k,
+                                 const float* beta, const void* bank_hi, const void* bank_lo, const void* bank_rows,
+                                 float bank_scale, const void* norm_plane, const int32_t* idx, const float* logw,
+                                 int64_t n_sel, int splits, int passes, int variant, int qi0, int qj0, int qrows,
+                                 int qcols, float* m, float* l, float* acc, float* dbg_dots, void* stream);
 /* 1 when the P.V epilogue supports the geometry */
 int cds_els_umma_pv_supported(int C, int H, int W, int k, int passes, int bank_planes);
 /* dynamic shared memory the umma kernel needs for this geometry (0 = unsupported geometry) */

@@ -290,6 +290,38 @@ def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs, variant):
         assert np.max(np.abs(mu - mu_o)) < MU_TOL, (b, np.max(np.abs(mu - mu_o)))
 
 
+@pytest.mark.parametrize("C,H,N,k,t,precision", [
+    (3, 32, 40, 17, 0.90, "f16"), (3, 32, 40, 17, 0.90, "auto"), (3, 32, 40, 17, 0.45, "f16x2"),
+    (3, 32, 33, 3, 0.10, "f16x2"), (3, 32, 33, 5, 0.30, "auto"), (3, 32, 33, 9, 0.60, "auto"), (3, 32, 33, 13, 0.75, "auto"),
+    (3, 32, 21, 25, 0.95, "auto"), (3, 32, 21, 31, 0.97, "f16"), (1, 28, 50, 7, 0.45, "auto"), (1, 28, 50, 23, 0.9, "auto"),
+    (2, 24, 30, 11, 0.6, "f16x2"), (3, 64, 12, 9, 0.6, "auto"), (3, 64, 12, 17, 0.9, "auto"),
+])
+def test_bbels_edge_bands_on_tensor_cores(C, H, N, k, t, precision):
+    """bbELS with the edge bands on the tcgen05 kernel (all depths of a band stacked on the query side of one contraction)
+    and the centre restricted to its query window: against the float64 oracle, and against the exact fp32 SIMT edge
+    kernel + full-image centre (the round-1 path).  Reference: idealscore.py:156-372."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
+    bank, labels = synthetic_bank(N, C, H, nlabels=3, seed=31)
+    beta = float(so.cosine_beta(t))
+    B = 2
+    x = noisy_query(bank, beta, B, seed=9)
+    mod = _make("bbELS", (bank, labels), k, 16, None, precision=precision)
+    eng = mod.engine("cuda")
+    passes = eng.passes_for(k, beta)
+    assert eng.edge_umma_supported(k, passes), "this geometry is expected on the tensor-core edge kernel"
+    dev = torch.device("cuda")
+    s_tc = mod(torch.full((B,), t), x.cuda(), device=dev).cpu().double().numpy()
+    eng.edge_variant, eng.centre_window = "simt", False
+    s_simt = mod(torch.full((B,), t), x.cuda(), device=dev).cpu().double().numpy()
+    for b in range(B):
+        mu = _mu_from_score(s_tc[b], x[b].double().numpy(), beta)
+        mu_s = _mu_from_score(s_simt[b], x[b].double().numpy(), beta)
+        mu_o = _oracle_mu("bbELS", x[b].numpy(), bank.numpy(), labels.numpy(), None, beta, k, 16)
+        assert np.max(np.abs(mu - mu_o)) < MU_TOL, (b, np.max(np.abs(mu - mu_o)))
+        assert np.max(np.abs(mu - mu_s)) < MU_TOL, (b, np.max(np.abs(mu - mu_s)))
+
+
 @pytest.mark.parametrize("precision", ["f16", "f16x2"])
 @pytest.mark.parametrize("C,H,k,t", [(3, 32, 9, 0.55), (3, 32, 11, 0.65), (3, 32, 13, 0.75), (3, 32, 17, 0.9),
                                      (3, 32, 19, 0.9), (1, 28, 9, 0.5), (1, 28, 13, 0.7), (2, 24, 11, 0.6)])
