@@ -411,7 +411,8 @@ def roofline(w, args, cd, mod, machine, eng, evals, scales, x0, dev, peaks, B):
         beta = torch.full((B,), beta_val, device=dev)
         x = x_at[i]
         if w["kind"] == "LS":
-            fn = lambda: eng.ls_partials(x, beta, k, sel)
+            passes = eng.passes_for(k, beta_val)
+            fn = lambda: eng.ls_partials(x, beta, k, sel, passes=passes)
         elif w["kind"] == "ELS":
             passes = eng.passes_for(k, beta_val)
             aob = eng._a_over_beta(beta_val)
@@ -443,7 +444,7 @@ def roofline(w, args, cd, mod, machine, eng, evals, scales, x0, dev, peaks, B):
         tot_bytes += n_c * w["C"] * w["H"] * w["H"] * eng.bank.ls_bytes_per_pixel() * count
     if w["bound"] == "hbm":
         achieved = tot_bytes / tot_ms * 1e-6                 # GB/s
-        return {"bound": "hbm", "kernel": "ls_rows_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+        return {"bound": "hbm", "kernel": "ls_umma_kernel" if eng.ls_umma_supported(w["k"], 1) else "ls_rows_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm"], "peak_source": peaks["source"], "traffic": None,
                 "note": f"algorithmic bytes = selected images x C*H*W x {eng.bank.ls_bytes_per_pixel()} B (the bank streamed once per "
                         f"evaluation for all {B} samples) / CUDA-event kernel time", "per_k": per_k}

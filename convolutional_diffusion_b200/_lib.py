@@ -32,6 +32,12 @@ SIGNATURES = {
     "cds_ls_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_ls_rows_supported": (_i, [_i, _i, _i, _i]),
     "cds_ls_rows_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "cds_ls_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "cds_ls_plane_elems": (_i64, [_i64, _i, _i]),
+    "cds_ls_norms_elems": (_i64, [_i64, _i, _i]),
+    "cds_pack_flat16": (_i, [_p, _i64, _i, _i, _i, _f, _p, _p]),
+    "cds_pack_ls_norms": (_i, [_p, _i64, _i, _i, _i, _i, _p, _p]),
+    "cds_ls_partials_umma": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
     "cds_bbels_edge_supported": (_i, [_i, _i, _i, _i]),
     "cds_bbels_edge_partials": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "cds_bbels_edge_umma_smem_bytes": (_i64, [_i, _i, _i, _i, _i]),

@@ -84,6 +84,8 @@ class PatchBank:
         self._nplane = {}
         self._eplane = None
         self._enorms = {}
+        self._flat16 = None
+        self._lsnorms = {}
         self._sel = {}
 
     # ---- layouts -------------------------------------------------------------------------------
@@ -166,6 +168,32 @@ class PatchBank:
                                                         _lib.ptr(out), _lib.stream_ptr()), "cds_pack_edge_norms")
                 self._enorms[k] = out
         return self._enorms[k]
+
+    def flat16(self):
+        """fp16 [N][HWp] flattened single-channel images (pixel * scale, rows padded to whole 16-byte granules) for the
+        tensor-core LS kernel; None for a two-plane or multi-channel bank."""
+        hi, lo, scale = self.strip8()
+        if lo is not None or self.C != 1:
+            return None
+        if self._flat16 is None:
+            with torch.cuda.device(self.device):
+                n = int(self.lib.cds_ls_plane_elems(self.N_local, self.H, self.W))
+                out = torch.empty(n, dtype=torch.float16, device=self.device)
+                _lib.check(self.lib.cds_pack_flat16(_lib.ptr(self.images), self.N_local, self.C, self.H, self.W, scale,
+                                                    _lib.ptr(out), _lib.stream_ptr()), "cds_pack_flat16")
+                self._flat16 = out
+        return self._flat16
+
+    def ls_norms(self, k):
+        """fp32 [N][128*ceil(HW/128)] zero-padded k x k window sums of T^2 (computed once per k) for the tensor-core LS kernel."""
+        if k not in self._lsnorms:
+            with torch.cuda.device(self.device):
+                n = int(self.lib.cds_ls_norms_elems(self.N_local, self.H, self.W))
+                out = torch.empty(n, dtype=torch.float32, device=self.device)
+                _lib.check(self.lib.cds_pack_ls_norms(_lib.ptr(self.images), self.N_local, self.C, self.H, self.W, k,
+                                                      _lib.ptr(out), _lib.stream_ptr()), "cds_pack_ls_norms")
+                self._lsnorms[k] = out
+        return self._lsnorms[k]
 
     def ls_bytes_per_pixel(self):
         """Bytes per bank pixel the LS kernels stream from HBM (algorithmic bytes of the roofline)."""

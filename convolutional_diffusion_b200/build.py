@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcdscore.so")
-SOURCES = ["api.cu", "simt_kernels.cu", "ls_kernel.cu", "ls_rows_kernel.cu", "bbels_edge.cu", "bbels_edge_umma.cu", "els_umma.cu"]
+SOURCES = ["api.cu", "simt_kernels.cu", "ls_kernel.cu", "ls_rows_kernel.cu", "bbels_edge.cu", "bbels_edge_umma.cu", "ls_umma.cu", "els_umma.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]      # --threads 0: compile the sources in parallel
 

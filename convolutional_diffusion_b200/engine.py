@@ -51,6 +51,7 @@ class ScoreEngine:
         # faster: k <= 9 and a/beta <= 100), "fma" (weighted sum on the FMA pipe), "pv" (P.V wherever supported); CDS_ELS_VARIANT overrides
         self.els_variant = os.environ.get("CDS_ELS_VARIANT", "auto")
         self.centre_window = os.environ.get("CDS_CENTRE_WINDOW", "1") != "0"   # A/B switch: 0 = centre kernel over all pixels
+        self.ls_variant = os.environ.get("CDS_LS_VARIANT", "auto")           # "simt": keep LS off the tensor cores
         self.edge_variant = os.environ.get("CDS_EDGE_VARIANT", "auto")       # "simt": keep the bbELS edge bands off the tensor cores
         if self.els_variant not in _lib.ELS_VARIANT:
             raise ValueError(f"CDS_ELS_VARIANT must be one of {sorted(_lib.ELS_VARIANT)}, got {self.els_variant!r}")
@@ -149,13 +150,30 @@ class ScoreEngine:
         smem = (8 if b.C == 1 else 4) * 4 * (b.H * (b.W + 2 * d) + (b.H + 2 * d) * b.W)   # images per round
         return b.C in (1, 3) and b.H * b.W <= 4096 and smem <= 227 * 1024
 
-    def ls_partials(self, x, beta, k, sel, tag="ls"):
-        """Bank-streaming LS kernel (csrc/ls_kernel.cu): the bank slice of every CTA is read once."""
+    def ls_umma_supported(self, k, passes):
+        """Tensor-core LS: single-channel 8-bit-exact bank, a window smaller than the image, query band fits shared memory."""
+        b = self.bank
+        return (self.use_tensor_cores and self.ls_variant != "simt" and b.C == 1 and b.strip8()[1] is None
+                and self.lib.cds_ls_umma_smem_bytes(b.C, b.H, b.W, k, passes) > 0)
+
+    def ls_partials(self, x, beta, k, sel, tag="ls", passes=None):
+        """LS partials: the tensor-core kernel (csrc/ls_umma.cu) when `passes` is given and the geometry is supported, else the
+        bank-streaming SIMT kernels (csrc/ls_rows_kernel.cu, csrc/ls_kernel.cu)."""
         idx, logw, n_sel = sel
         if n_sel == 0:
             return self._empty_shard(tag, x.shape[0])
         b = self.bank
         B = x.shape[0]
+        if passes is not None and self.ls_umma_supported(k, passes):
+            mt = (b.H * b.W + 127) // 128
+            S = self._splits(mt, B, n_sel, waves=2, min_images=128)
+            P = self._partials(tag, S, B)
+            _lib.check(self.lib.cds_ls_partials_umma(
+                _lib.ptr(x), B, b.C, b.H, b.W, k, _lib.ptr(beta), _lib.ptr(b.flat16()), b.strip8()[2], _lib.ptr(b.ls_norms(k)),
+                _lib.ptr(idx), _lib.ptr(logw), n_sel, S, passes, _lib.ptr(P.m), _lib.ptr(P.l), _lib.ptr(P.acc),
+                _lib.stream_ptr()), "cds_ls_partials_umma")
+            self.launches += 1
+            return P
         rows = bool(self.lib.cds_ls_rows_supported(b.C, b.H, b.W, k))
         sb = 2 if rows else 4                                   # samples per CTA of the two kernels
         S = int(min(n_sel, max(1, (2 * sm_count(self.device)) // ((B + sb - 1) // sb))))
@@ -308,7 +326,10 @@ class ScoreEngine:
         if kind == "LS":
             # use_tensor_cores=False asks for the generic exact-fp32 kernel; the streaming LS kernels are fp32 SIMT as
             # well and take over where the generic one cannot hold the padded planes (IS on images above 32 pixels)
-            if self.ls_supported(k) and (self.use_tensor_cores or not self.simt_supported(k)):
+            passes = self.passes_for(k, beta_min)
+            if self.ls_umma_supported(k, passes):
+                P = self.ls_partials(x, beta, k, sel, passes=passes)
+            elif self.ls_supported(k) and (self.use_tensor_cores or not self.simt_supported(k)):
                 P = self.ls_partials(x, beta, k, sel)
             else:
                 P = self.simt_partials("LS", "zeros", x, beta, k, sel)

@@ -84,6 +84,21 @@ int cds_ls_rows_partials(const float* x, int B, int C, int H, int W, int k, cons
                          const int32_t* idx, const float* logw, int64_t n_sel, int splits, float* m, float* l,
                          float* acc, void* stream);
 
+/* LS on the tensor cores (tcgen05, csrc/ls_umma.cu; single-channel images, 3 <= k < 2*max(H,W)-1): the window sum of x.T_n is
+ * the contraction of a banded query matrix A[y][z] = x(z)*[z in win(y)] with the flattened image, M = 128 pixels, K = the
+ * image rows their windows touch, N = images (transposed on the fly by cp.async); the window sums of T_n^2 come from a per-k
+ * fp32 plane.  Bank side, packed once: cds_pack_flat16 ([n][cds_ls_plane_elems/N] fp16 pixel*scale, same scale as
+ * cds_pack_strip8, single exact plane) and cds_pack_ls_norms ([n][cds_ls_norms_elems/N] fp32).  passes as in cds_els_partials_umma.
+ * cds_ls_umma_smem_bytes = 0: geometry not supported (use cds_ls_rows_partials / cds_ls_partials). */
+int64_t cds_ls_umma_smem_bytes(int C, int H, int W, int k, int passes);
+int64_t cds_ls_plane_elems(int64_t N, int H, int W);
+int64_t cds_ls_norms_elems(int64_t N, int H, int W);
+int cds_pack_flat16(const float* images, int64_t N, int C, int H, int W, float scale, void* out_f16, void* stream);
+int cds_pack_ls_norms(const float* images, int64_t N, int C, int H, int W, int k, float* out, void* stream);
+int cds_ls_partials_umma(const float* x, int B, int C, int H, int W, int k, const float* beta, const void* flat16,
+                         float scale, const float* ls_norms, const int32_t* idx, const float* logw, int64_t n_sel,
+                         int splits, int passes, float* m, float* l, float* acc, void* stream);
+
 /* bbELS edge bands (idealscore.py:256-288): queries whose patch crosses exactly one border vs the zero-padded
  * patches at the same depth and every interior position along the band.  Exact fp32; square images, odd k <= 31.
  * Writes the partials of the edge pixels only. */

@@ -290,6 +290,36 @@ def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs, variant):
         assert np.max(np.abs(mu - mu_o)) < MU_TOL, (b, np.max(np.abs(mu - mu_o)))
 
 
+@pytest.mark.parametrize("H,N,k,t,precision,label", [
+    (28, 200, 5, 0.80, "auto", None), (28, 200, 5, 0.15, "auto", 1), (28, 131, 3, 0.05, "f16x2", None),
+    (28, 131, 9, 0.60, "auto", 2), (28, 131, 17, 0.90, "f16", None), (28, 70, 27, 0.95, "auto", None),
+    (32, 90, 7, 0.45, "auto", None), (16, 77, 11, 0.70, "f16x2", 0), (20, 64, 5, 0.30, "auto", None),
+])
+def test_ls_on_tensor_cores(H, N, k, t, precision, label):
+    """Single-channel LS through the tcgen05 kernel (banded query matrix in TMEM, images transposed on the fly) against the
+    float64 oracle and against the exact fp32 SIMT bank-streaming kernel.  Reference: idealscore.py:497-557."""
+    from oracle import score_oracle as so
+    from convolutional_diffusion_b200.synthetic import synthetic_bank, noisy_query
+    bank, labels = synthetic_bank(N, 1, H, nlabels=3, seed=17)
+    beta = float(so.cosine_beta(t))
+    B = 3
+    x = noisy_query(bank, beta, B, seed=4)
+    mod = _make("LS", (bank, labels), k, N, None, precision=precision)
+    eng = mod.engine("cuda")
+    assert eng.ls_umma_supported(k, eng.passes_for(k, beta)), "this geometry is expected on the tensor-core LS kernel"
+    dev = torch.device("cuda")
+    lab = None if label is None else torch.tensor([label])
+    s_tc = mod(torch.full((B,), t), x.cuda(), label=lab, device=dev).cpu().double().numpy()
+    eng.ls_variant = "simt"
+    s_simt = mod(torch.full((B,), t), x.cuda(), label=lab, device=dev).cpu().double().numpy()
+    for b in range(B):
+        mu = _mu_from_score(s_tc[b], x[b].double().numpy(), beta)
+        mu_s = _mu_from_score(s_simt[b], x[b].double().numpy(), beta)
+        mu_o = _oracle_mu("LS", x[b].numpy(), bank.numpy(), labels.numpy(), label, beta, k, N)
+        assert np.max(np.abs(mu - mu_o)) < MU_TOL, (b, np.max(np.abs(mu - mu_o)))
+        assert np.max(np.abs(mu - mu_s)) < MU_TOL, (b, np.max(np.abs(mu - mu_s)))
+
+
 @pytest.mark.parametrize("C,H,N,k,t,precision", [
     (3, 32, 40, 17, 0.90, "f16"), (3, 32, 40, 17, 0.90, "auto"), (3, 32, 40, 17, 0.45, "f16x2"),
     (3, 32, 33, 3, 0.10, "f16x2"), (3, 32, 33, 5, 0.30, "auto"), (3, 32, 33, 9, 0.60, "auto"), (3, 32, 33, 13, 0.75, "auto"),
