@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
         float t[16], cmax = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          t[e] = fmaf(__uint_as_float(v[e]), cs, fmaf(p2[(c0 + e) * 128], cn, lws[c0 + e]));   // lw = -inf masks a missing image
+          // images past the end of the slice: their norms were never fetched (whatever the buffer holds, possibly NaN patterns)
+          t[e] = c0 + e < nv ? fmaf(__uint_as_float(v[e]), cs, fmaf(p2[(c0 + e) * 128], cn, lws[c0 + e])) : -INFINITY;
           cmax = fmaxf(cmax, t[e]);
         }
         if (cmax > m) {

@@ -294,6 +294,7 @@ def test_seeded_against_oracle(kind, C, H, N, k, t, label, bs, variant):
     (28, 200, 5, 0.80, "auto", None), (28, 200, 5, 0.15, "auto", 1), (28, 131, 3, 0.05, "f16x2", None),
     (28, 131, 9, 0.60, "auto", 2), (28, 131, 17, 0.90, "f16", None), (28, 70, 27, 0.95, "auto", None),
     (32, 90, 7, 0.45, "auto", None), (16, 77, 11, 0.70, "f16x2", 0), (20, 64, 5, 0.30, "auto", None),
+    (12, 9, 13, 0.95, "auto", None), (12, 5, 3, 0.20, "auto", None),          # fewer images than one tile
 ])
 def test_ls_on_tensor_cores(H, N, k, t, precision, label):
     """Single-channel LS through the tcgen05 kernel (banded query matrix in TMEM, images transposed on the fly) against the
