@@ -146,6 +146,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
+  // the norms of images past the end of a slice are never fetched; their columns are masked by lw = -inf, which only works on
+  // finite values: start from zeros (later tiles leave finite stale data)
+  for (int e = tid * 16; e < 2 * g.buf_bytes; e += LS_THREADS * 16) *reinterpret_cast<uint4*>(sBuf + e) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -304,11 +308,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
         tmem_ld16(tmem_base + lane_addr + s * G + c0, v);
         tmem_ld_wait16(v);
         if (c0 >= nv || (p.flags & 1)) continue;            // warp-uniform
-        float t[16], cmax = -INFINITY;
+        float t[16], lw[16], cmax = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(lw + e) = *reinterpret_cast<const float4*>(lws + c0 + e);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          // images past the end of the slice: their norms were never fetched (whatever the buffer holds, possibly NaN patterns)
-          t[e] = c0 + e < nv ? fmaf(__uint_as_float(v[e]), cs, fmaf(p2[(c0 + e) * 128], cn, lws[c0 + e])) : -INFINITY;
+          t[e] = fmaf(__uint_as_float(v[e]), cs, fmaf(p2[(c0 + e) * 128], cn, lw[e]));   // lw = -inf masks a missing image
           cmax = fmaxf(cmax, t[e]);
         }
         if (cmax > m) {

@@ -32,6 +32,19 @@ def main():
             err = float((s0 - s1).abs().max())
             worst = max(worst, err)
             assert err < 1e-3, (cls.__name__, label, err)
+    # single-channel bank: LS goes through the tensor-core kernel (rank-local flat16 / norm planes)
+    bank1, labels1 = synthetic_bank(2000, 1, 28, nlabels=10, seed=1)
+    x1 = torch.randn(2, 1, 28, 28, generator=torch.Generator().manual_seed(5)).to(dev)
+    kw = dict(kernel_size=5, batch_size=2000, image_size=28, schedule=cosine_noise_schedule, precision="auto")
+    full = LocalScoreModule((bank1, labels1), **kw)
+    shard = LocalScoreModule((bank1, labels1), process_group=dist.group.WORLD, **kw)
+    assert shard.engine(dev).ls_umma_supported(5, 1)
+    for label in (None, torch.tensor([3])):
+        s0 = full(torch.full((2,), 0.5), x1, label=label, device=dev)
+        s1 = shard(torch.full((2,), 0.5), x1, label=label, device=dev)
+        err = float((s0 - s1).abs().max())
+        worst = max(worst, err)
+        assert err < 1e-3, ("LS C=1", label, err)
     # a class with a single image: with two ranks one shard is empty and must contribute the neutral element
     few_labels = labels.clone()
     few_labels[few_labels == 9] = 0
