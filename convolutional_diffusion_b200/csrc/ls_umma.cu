@@ -27,7 +27,9 @@
 namespace {
 using namespace umma;
 
-constexpr int LS_THREADS = 416;     // warps 0-3 epilogue, 4-7 transposers, 8 MMA issuer, 9-10 band fetchers, 11-12 norm fetchers
+// warps 0-3 epilogue (even 16-column chunks), 4-7 transposers, 8 MMA issuer, 9-10 band fetchers, 11-12 norm fetchers,
+// 13-16 epilogue (odd chunks; warp & 3 = TMEM lane quadrant), 17-20 transposers
+constexpr int LS_THREADS = 672;
 
 #ifdef CDS_PROFILE_SWITCHES
 __device__ long long g_ls_clk[8][64];
@@ -138,10 +140,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_rfull + 8 * s, 2);       // the two band fetcher warps (expect_tx each)
       mbar_init(bar_pfull + 8 * s, 2);       // the two norm fetcher warps
-      mbar_init(bar_rfree + 8 * s, 4);       // the four transposer warps
-      mbar_init(bar_bfull + 8 * s, 4);
+      mbar_init(bar_rfree + 8 * s, 8);       // the eight transposer warps
+      mbar_init(bar_bfull + 8 * s, 8);
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_done + 8 * s, 4);
+      mbar_init(bar_done + 8 * s, 8);       // the eight epilogue warps
     }
     fence_barrier_init();
   }
@@ -188,13 +190,18 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= 4 && warp < 8) {
+  if ((warp >= 4 && warp < 8) || warp >= 17) {
     // ---------------------------------------------------------------- transposers: raw band [image][granule] -> [granule][image]
-    const int tt = tid - 128;
-    const int tpi = 128 / G, n = tt / tpi, part = tt - n * tpi;
+    const int tt = warp < 8 ? tid - 128 : tid - 17 * 32 + 128;       // 0..255
+    const int tpi = 256 / G, n = tt / tpi, part = tt - n * tpi;
+    auto logw_of = [&](int T) -> float {      // log-weight of this thread's image in tile T, fetched one tile ahead
+      return (T < tiles && part == 0 && n < min(G, n_img - T * G)) ? __ldg(p.logw + n0 + (long long)T * G + n) * CDS_LOG2E : -INFINITY;
+    };
+    float lw_cur = logw_of(0);
     for (int T = 0; T < tiles; ++T) {
       const int s = T & 1;
       const int nv = min(G, n_img - T * G);
+      const float lw_next = logw_of(T + 1);
       mbar_wait(bar_rfull + 8 * s, (T >> 1) & 1, 1);
       if (tt == 0) LS_STAMP(0, T);
       mbar_wait(bar_done + 8 * s, ((T >> 1) & 1) ^ 1, 2);         // tile T-2 has left the transposed buffer
@@ -216,7 +223,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
       } else {
         for (int kg = part; kg < KGt; kg += tpi) *reinterpret_cast<uint4*>(bc + (size_t)kg * g.b_row + (size_t)n * 16) = make_uint4(0, 0, 0, 0);
       }
-      if (part == 0) lws[n] = n < nv ? __ldg(p.logw + n0 + (long long)T * G + n) * CDS_LOG2E : -INFINITY;
+      if (part == 0) lws[n] = lw_cur;
+      lw_cur = lw_next;
       fence_proxy_async();           // the UMMAs read the band, and the next bulk copy overwrites the raw slot, through the async proxy
       __syncwarp();
       if (lane == 0) {
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) LS_STAMP(5, T);
     }
-  } else if (warp >= 9) {
+  } else if (warp >= 9 && warp < 13) {
     // ---------------------------------------------------------------- fetchers: one bulk copy per image and tile.  Issuing a bulk
     // copy costs a warp ~65 cycles per lane (measured), so the 2*G copies of a tile are spread over four warps that do nothing
     // else: warps 9-10 the raw bands (slot free once the four transposer warps have read it), warps 11-12 the window norms of the
@@ -285,9 +293,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
     }
   } else {
     // ---------------------------------------------------------------- epilogue: thread = pixel
-    const int yl = tid, y = 128 * mt + yl;
+    // two warpgroups share every tile: group 0 (warps 0-3) takes the even 16-column chunks, group 1 (warps 13-16) the odd ones; each
+    // keeps its own softmax state per pixel, merged once at the end
+    const int wg = warp < 4 ? 0 : 1;
+    const int yl = (warp & 3) * 32 + lane, y = 128 * mt + yl;
     const float cs = a * CDS_LOG2E / (beta * p.scale), cn = -(1.f - beta) * CDS_LOG2E / (2.f * beta);
-    const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     const int zr = min(max(y - zlo8, 0), KGt * 8 - 1);     // this pixel inside the band: granule zr/8, slot zr%8
     const int voff = (zr >> 3) * g.b_row + (zr & 7) * 2;
     float m = -INFINITY, l = 0.f, acc = 0.f;
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
       const uint8_t* bc = sBuf + (size_t)s * g.buf_bytes;
       const float* p2 = reinterpret_cast<const float*>(bc + g.b_bytes) + yl;
       const float* lws = reinterpret_cast<const float*>(bc + g.b_bytes + g.p2_bytes);
-      for (int c0 = 0; c0 < G; c0 += 16) {
+      for (int c0 = 16 * wg; c0 < G; c0 += 32) {
         uint32_t v[16];
         __syncwarp();
         tmem_ld16(tmem_base + lane_addr + s * G + c0, v);
@@ -334,9 +345,24 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
       if (lane == 0) mbar_arrive(bar_done + 8 * s);
       if (tid == 0) LS_STAMP(7, T);
     }
-    if (y < HW) {
+    // merge the two groups' states (the raw ring is idle by now: every tile has been transposed and contracted)
+    float* sMerge = reinterpret_cast<float*>(sRaw);
+    if (wg == 1) {
+      sMerge[yl * 3] = m;
+      sMerge[yl * 3 + 1] = l;
+      sMerge[yl * 3 + 2] = acc;
+    }
+    bar_sync_named(2, 256);
+    if (wg == 0 && y < HW) {
+      const float m1 = sMerge[yl * 3], l1 = sMerge[yl * 3 + 1], a1 = sMerge[yl * 3 + 2];
+      const float M = fmaxf(m, m1);
+      if (M > -INFINITY) {
+        const float w0 = ex2(m - M), w1 = ex2(m1 - M);        // ex2(-inf) = 0: an empty side drops out
+        l = fmaf(l, w0, l1 * w1);
+        acc = fmaf(acc, w0, a1 * w1);
+      }
       const size_t o = ((size_t)split * p.B + b) * HW + y;
-      p.m[o] = m;
+      p.m[o] = M;
       p.l[o] = l;
       p.acc[o] = acc / p.scale;
     }
