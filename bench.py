@@ -63,6 +63,19 @@ WORKLOADS = {
 T_OF_K = {3: 0.10, 5: 0.25, 7: 0.45, 9: 0.60, 11: 0.70, 13: 0.75, 15: 0.80, 17: 0.90}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures of
+# the same workload (a bench run cannot measure it: nothing printed under a profiler is a bench value).  Algorithmic bank bytes
+# for comparison: headline 5 000 images x 48 KB of strip8 + 16 KB of norm plane = 0.32 GB per launch.
+NCU_TRAFFIC = {
+    "els_cifar10_conditional": {"bytes": 712.2e6, "source": "profiles/r02_els_umma_ncu_summary.md: k=17 launch of the headline "
+                                "trajectory at batch 4 (705.5 MB read + 6.7 MB written; k=5: 620 MB, k=7: 592 MB); not re-measured by this run"},
+    "bbels_cifar10_k17": {"bytes": 1030.4e6, "source": "profiles/r02_bbels_edge_umma_ncu_summary.md: the edge-band launch "
+                          "(1 024.8 MB read + 5.7 MB written = the algorithmic 1.024 GB); not re-measured by this run"},
+    "ls_mnist": {"bytes": 314.2e6, "source": "profiles/r02_ls_umma_ncu_summary.md: one B=10 evaluation (310.6 MB read + 3.5 MB written = "
+                 "the unique fp16 image + fp32 norm bytes); not re-measured by this run"},
+}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -445,16 +458,16 @@ def roofline(w, args, cd, mod, machine, eng, evals, scales, x0, dev, peaks, B):
     if w["bound"] == "hbm":
         achieved = tot_bytes / tot_ms * 1e-6                 # GB/s
         return {"bound": "hbm", "kernel": "ls_umma_kernel" if eng.ls_umma_supported(w["k"], 1) else "ls_rows_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm"], "peak_source": peaks["source"], "traffic": None,
+                "frac": achieved / peaks["hbm"], "peak_source": peaks["source"],
+                "traffic": NCU_TRAFFIC.get(w["name"], {}).get("bytes"), "traffic_source": NCU_TRAFFIC.get(w["name"], {}).get("source"),
                 "note": f"algorithmic bytes = selected images x C*H*W x {eng.bank.ls_bytes_per_pixel()} B (the bank streamed once per "
                         f"evaluation for all {B} samples) / CUDA-event kernel time", "per_k": per_k}
     achieved = tot_fl / tot_ms * 1e-9
     out = {"bound": "tensor", "kernel": "els_umma_kernel" if w["kind"] == "ELS" else "bbELS: els_umma_kernel (centre window) + bbels_edge_umma_kernel (edge bands) + ls_rows_kernel (corners)",
            "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
            "frac_sustained": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"],
-           "traffic": 712.0e6 if w["name"] == "els_cifar10_conditional" else None,
-           "traffic_source": "ncu --set full capture of round 1 at batch 4, class 0, k=17 (profiles/r01g_els_umma_ncu_summary.md), "
-                             "not re-measured by this run" if w["name"] == "els_cifar10_conditional" else None,
+           "traffic": NCU_TRAFFIC.get(w["name"], {}).get("bytes"),
+           "traffic_source": NCU_TRAFFIC.get(w["name"], {}).get("source"),
            "note": "algorithmic 2 FLOP per patch element and (query, patch) pair (2*k*k*C for ELS; truncated patches counted as such for bbELS edges/corners), FLOP-weighted over the evaluations of one step, each on the "
                    "x of its own step; CUDA events around the launches on the launching stream", "per_k": per_k}
     if w["name"] == "bbels_cifar10_k17":                     # the ELS / circular counterpart of configs[3]
