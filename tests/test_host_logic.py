@@ -122,6 +122,28 @@ def test_library_exports_every_declared_symbol():
     assert loaded.cds_els_umma_smem_bytes(3, 32, 32, 4, 1, 1) == 0       # even kernel sizes are rejected
 
 
+def test_edge_and_ls_tensor_core_geometries():
+    """Host-only geometry queries of the tensor-core bbELS edge-band and LS kernels: what is supported fits 227 KB of shared
+    memory, what is not reports 0 (the engine then keeps the exact SIMT kernels)."""
+    lib = _lib.load()
+    for H, C in ((32, 3), (28, 1), (64, 3)):
+        for k in range(3, min(H, 28), 2):
+            assert 0 < lib.cds_bbels_edge_umma_smem_bytes(C, H, H, k, 1) <= 227 * 1024, (H, C, k)
+    assert 0 < lib.cds_bbels_edge_umma_smem_bytes(3, 32, 32, 17, 2) <= 227 * 1024      # cfg-4 with two query passes
+    assert lib.cds_bbels_edge_umma_smem_bytes(3, 32, 32, 31, 2) == 0                      # query blocks too large: SIMT kernel
+    assert lib.cds_bbels_edge_umma_smem_bytes(3, 32, 24, 7, 1) == 0                       # square images only
+    assert lib.cds_bbels_edge_umma_smem_bytes(3, 32, 32, 32, 1) == 0                      # k >= H is the LS delegate
+    assert lib.cds_edge_plane_halves(10, 3, 32) == 10 * 4 * 3 * 4 * 32 * 8
+    assert lib.cds_edge_norms_halves(10, 32, 17) == 10 * 4 * 8 * 16 * 8
+    for k in (3, 5, 9, 17, 27):
+        assert 0 < lib.cds_ls_umma_smem_bytes(1, 28, 28, k, 1) <= 227 * 1024, k            # cfg-1 shapes, one query pass
+    assert 0 < lib.cds_ls_umma_smem_bytes(1, 28, 28, 5, 2) <= 227 * 1024
+    assert lib.cds_ls_umma_smem_bytes(1, 28, 28, 17, 2) == 0      # two planes of the query operand exceed TMEM: SIMT kernel
+    assert lib.cds_ls_umma_smem_bytes(3, 32, 32, 5, 1) == 0       # multi-channel LS (bbELS corners) stays on the SIMT kernel
+    assert lib.cds_ls_umma_smem_bytes(1, 28, 28, 55, 1) == 0      # whole-image window (IS)
+    assert lib.cds_ls_plane_elems(7, 28, 28) == 7 * 792 and lib.cds_ls_norms_elems(7, 28, 28) == 7 * 896
+
+
 def _umma_geometries(ks, variant, passes=1):
     """Runs the geometry selection of cds_els_partials_umma (printed with CDS_DEBUG_GEOM) in a subprocess without a
     GPU: the launch itself fails, the pointers are dummies."""
