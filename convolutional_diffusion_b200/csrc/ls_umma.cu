@@ -27,8 +27,8 @@
 namespace {
 using namespace umma;
 
-// warps 0-3 epilogue (even 16-column chunks), 4-7 transposers, 8 MMA issuer, 9-10 band fetchers, 11-12 norm fetchers,
-// 13-16 epilogue (odd chunks; warp & 3 = TMEM lane quadrant), 17-20 transposers
+// warps 0-3 epilogue (even 16-column chunks), 4-7 transposers, 8 MMA issuer, 9-12 band fetchers, 13-16 epilogue (odd chunks;
+// warp & 3 = TMEM lane quadrant), 17-20 norm fetchers
 constexpr int LS_THREADS = 672;
 
 #ifdef CDS_PROFILE_SWITCHES
@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_rfull + 8 * s, 2);       // the two band fetcher warps (expect_tx each)
-      mbar_init(bar_pfull + 8 * s, 2);       // the two norm fetcher warps
-      mbar_init(bar_rfree + 8 * s, 8);       // the eight transposer warps
-      mbar_init(bar_bfull + 8 * s, 8);
+      mbar_init(bar_rfull + 8 * s, 4);       // the four band fetcher warps (expect_tx each)
+      mbar_init(bar_pfull + 8 * s, 4);       // the four norm fetcher warps
+      mbar_init(bar_rfree + 8 * s, 4);       // the four transposer warps
+      mbar_init(bar_bfull + 8 * s, 4);
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_done + 8 * s, 8);       // the eight epilogue warps
     }
@@ -190,10 +190,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
 
-  if ((warp >= 4 && warp < 8) || warp >= 17) {
+  if (warp >= 4 && warp < 8) {
     // ---------------------------------------------------------------- transposers: raw band [image][granule] -> [granule][image]
-    const int tt = warp < 8 ? tid - 128 : tid - 17 * 32 + 128;       // 0..255
-    const int tpi = 256 / G, n = tt / tpi, part = tt - n * tpi;
+    const int tt = tid - 128;
+    const int tpi = 128 / G, n = tt / tpi, part = tt - n * tpi;
     auto logw_of = [&](int T) -> float {      // log-weight of this thread's image in tile T, fetched one tile ahead
       return (T < tiles && part == 0 && n < min(G, n_img - T * G)) ? __ldg(p.logw + n0 + (long long)T * G + n) * CDS_LOG2E : -INFINITY;
     };
@@ -259,37 +259,39 @@ __global__ void __launch_bounds__(LS_THREADS, 1) ls_umma_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) LS_STAMP(5, T);
     }
-  } else if (warp >= 9 && warp < 13) {
-    // ---------------------------------------------------------------- fetchers: one bulk copy per image and tile.  Issuing a bulk
-    // copy costs a warp ~65 cycles per lane (measured), so the 2*G copies of a tile are spread over four warps that do nothing
-    // else: warps 9-10 the raw bands (slot free once the four transposer warps have read it), warps 11-12 the window norms of the
-    // tile's 128 pixels, straight into place (free once the epilogue has released the buffer).
-    const bool band = warp < 11;
-    const int half = (warp - 9) & 1, per = G / 2;              // images [half*per, half*per + per) of the tile
+  } else if ((warp >= 9 && warp < 13) || warp >= 17) {
+    // ---------------------------------------------------------------- fetchers: one bulk copy per image and tile.  A warp gets a
+    // bulk copy out every ~100 cycles, whether its lanes issue one each or one lane loops (both measured), and the window norms of
+    // tile T can only be fetched once the epilogue has released the buffer of tile T-2: with two warps per plane (32 copies each)
+    // the norms of a tile landed 4 000 cycles after that release and the epilogue waited for them.  Four warps per plane: warps
+    // 9-12 the raw bands (slot free once the four transposer warps have read it), warps 17-20 the window norms of the tile's 128
+    // pixels, straight into place.
+    const bool band = warp < 13;
+    const int part = (warp - 9) & 3, per = G / 4;              // images [part*per, part*per + per) of the tile, per <= 32
     const uint32_t bar_free = band ? bar_rfree : bar_done, bar_full = band ? bar_rfull : bar_pfull;
     const uint32_t bytes = band ? (uint32_t)KGt * 16 : 512u;
     const size_t stride = band ? (size_t)g.HWp * 2 : (size_t)g.HWn * 4;
     const uint8_t* src0 = band ? reinterpret_cast<const uint8_t*>(p.plane + zlo8) : reinterpret_cast<const uint8_t*>(p.norms + 128 * mt);
     const uint32_t dst_stride = band ? (uint32_t)g.raw_stride : 512u;
-    auto lookup = [&](int T, int u) -> int {
-      const int q = half * per + lane + 32 * u;
-      return (T < tiles && lane + 32 * u < per && q < min(G, n_img - T * G)) ? p.idx[n0 + (long long)T * G + q] : -1;
+    auto lookup = [&](int T) -> int {
+      const int q = part * per + lane;
+      return (T < tiles && lane < per && q < min(G, n_img - T * G)) ? p.idx[n0 + (long long)T * G + q] : -1;
     };
-    int img0 = lookup(0, 0), img1 = lookup(0, 1);
+    int img0 = lookup(0), img1 = lookup(1);                    // index lookups run two tiles ahead
     for (int T = 0; T < tiles; ++T) {
       const int s = T & 1;
       const int nv = min(G, n_img - T * G);
-      const int mine = max(0, min(per, nv - half * per));
+      const int mine = max(0, min(per, nv - part * per));
+      const int img2 = lookup(T + 2);
       mbar_wait(bar_free + 8 * s, ((T >> 1) & 1) ^ 1, 7);
-      if (!band) fence_proxy_async();
       if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)mine * bytes);
       __syncwarp();
-      const uint32_t dst = band ? smem_u32(sRaw + (size_t)s * g.raw_bytes) : smem_u32(sBuf + (size_t)s * g.buf_bytes + g.b_bytes);
-      if (img0 >= 0) bulk_g2s(dst + (half * per + lane) * dst_stride, src0 + (size_t)img0 * stride, bytes, bar_full + 8 * s);
-      if (img1 >= 0) bulk_g2s(dst + (half * per + lane + 32) * dst_stride, src0 + (size_t)img1 * stride, bytes, bar_full + 8 * s);
+      const uint32_t dst = (band ? smem_u32(sRaw + (size_t)s * g.raw_bytes) : smem_u32(sBuf + (size_t)s * g.buf_bytes + g.b_bytes))
+                           + (part * per + lane) * dst_stride;
+      if (img0 >= 0) bulk_g2s(dst, src0 + (size_t)img0 * stride, bytes, bar_full + 8 * s);
       if (band && warp == 9 && lane == 0) LS_STAMP(3, T);
-      img0 = lookup(T + 1, 0);
-      img1 = lookup(T + 1, 1);
+      img0 = img1;
+      img1 = img2;
     }
   } else {
     // ---------------------------------------------------------------- epilogue: thread = pixel
