@@ -23,8 +23,8 @@
 // shifted by 8 granules.  k=17 on 32x32: 2*8 groups = 128 rows, one M tile, 55 K steps, N = 8*G candidates per
 // instruction (G images, one instruction per 8-position group h').
 //
-// CTA = (band, M tile, bank slice, sample); warps 0-3 epilogue (TMEM lane = query row), warp 4 producer (bulk copies of
-// the per-image granule rows + norm granules into a 2-stage ring), warp 5 MMA issuer (two TMEM accumulator buffers).
+// CTA = (band, M tile, bank slice, sample); warps 0-3 epilogue (TMEM lane = query row), warps 4-7 producers (bulk copies of
+// the per-image granule rows + norm granules into a 2-stage ring), warp 8 MMA issuer (two TMEM accumulator buffers).
 // passes = 1: fp16 query; 2: fp16 hi + lo residual of the query (the K steps of the strips run twice), as in the ELS kernel.
 // The bank must be a single exact fp16 plane; everything else stays on the SIMT kernel.
 #include "umma_common.cuh"
@@ -32,7 +32,7 @@
 namespace {
 using namespace umma;
 
-constexpr int EDGE_THREADS = 192;
+constexpr int EDGE_THREADS = 288;     // warps 0-3 epilogue, 4-7 producers (one per copy kind), 8 MMA issuer
 constexpr int EDGE_MAX_MMAS = 400;
 
 struct EdgeGeom {
@@ -171,13 +171,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) bbels_edge_umma_kernel(const 
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, C + 1);    // one producer warp per channel plane + one for the norms (expect_tx each)
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_done + 8 * s, 4);
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
+  if (warp == 8) tmem_alloc(smem_u32(sTmemBase), TMEM_COLS);
   // masked candidate columns and zero-weighted K slots read whatever lies in the ring: keep it finite
   for (int e = tid * 16; e < 2 * g.stage_bytes + 1024; e += EDGE_THREADS * 16)
     *reinterpret_cast<uint4*>(sStage + e) = make_uint4(0, 0, 0, 0);
@@ -229,30 +229,37 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) bbels_edge_umma_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *sTmemBase;
 
-  if (warp == 4) {
-    // ---------------------------------------------------------------- producer
-    const size_t img_bytes = (size_t)4 * C * g.NGRall * g.S1, band_bytes = (size_t)C * g.NGRall * g.S1;
-    const size_t nimg_bytes = (size_t)4 * g.norm_bytes;
-    const int per_c = g.NGR * g.S1;
-    for (int T = 0; T < tiles; ++T) {
-      const int s = T & 1;
-      mbar_wait(bar_done + 8 * s, ((T >> 1) & 1) ^ 1, 1);
-      const int nv = min(g.G, n_img - T * g.G);
-      if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)nv * (uint32_t)g.img_stride);
-      __syncwarp();
-      const uint32_t dst0 = smem_u32(sStage + (size_t)s * g.stage_bytes);
-      for (int e = lane; e < nv * (C + 1); e += 32) {
-        const int im = e / (C + 1), part = e % (C + 1);
-        const long long n = p.idx[n0 + (long long)T * g.G + im];
-        if (part < C)
-          bulk_g2s(dst0 + im * g.img_stride + part * per_c, p.plane + n * img_bytes + band * band_bytes + (size_t)part * g.NGRall * g.S1,
-                   (uint32_t)per_c, bar_full + 8 * s);
-        else
-          bulk_g2s(dst0 + im * g.img_stride + g.strip_bytes, p.norms + n * nimg_bytes + (size_t)band * g.norm_bytes,
-                   (uint32_t)g.norm_bytes, bar_full + 8 * s);
+  if (warp >= 4 && warp < 8) {
+    // ---------------------------------------------------------------- producers.  A warp gets a cp.async.bulk out every ~100
+    // cycles (measured in the LS kernel), so the (C+1) copies per image go to C+1 warps: warp 4+c the granule rows of channel c,
+    // warp 4+C the norm granules; one copy per lane and tile (G <= 16 images), index lookups one tile ahead.
+    const int part = warp - 4;
+    if (part <= C) {
+      const size_t img_bytes = (size_t)4 * C * g.NGRall * g.S1, band_bytes = (size_t)C * g.NGRall * g.S1;
+      const size_t nimg_bytes = (size_t)4 * g.norm_bytes;
+      const int per_c = g.NGR * g.S1;
+      const uint32_t bytes = part < C ? (uint32_t)per_c : (uint32_t)g.norm_bytes;
+      const uint8_t* src0 = part < C ? p.plane + band * band_bytes + (size_t)part * g.NGRall * g.S1 : p.norms + (size_t)band * g.norm_bytes;
+      const size_t stride = part < C ? img_bytes : nimg_bytes;
+      const uint32_t off = part < C ? (uint32_t)(part * per_c) : (uint32_t)g.strip_bytes;
+      auto lookup = [&](int T) -> long long {
+        return (T < tiles && lane < min(g.G, n_img - T * g.G)) ? (long long)p.idx[n0 + (long long)T * g.G + lane] : -1;
+      };
+      long long img = lookup(0);
+      for (int T = 0; T < tiles; ++T) {
+        const int s = T & 1;
+        const long long next = lookup(T + 1);
+        mbar_wait(bar_done + 8 * s, ((T >> 1) & 1) ^ 1, 1);
+        const int nv = min(g.G, n_img - T * g.G);
+        if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)nv * bytes);
+        __syncwarp();
+        if (img >= 0)
+          bulk_g2s(smem_u32(sStage + (size_t)s * g.stage_bytes) + lane * g.img_stride + off, src0 + (size_t)img * stride, bytes,
+                   bar_full + 8 * s);
+        img = next;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 8) {
     // ---------------------------------------------------------------- MMA issuer
     const uint64_t a_hi = desc_hi(g.RA), a_hi_n = desc_hi(128), b_hi = desc_hi(g.img_stride);
     const uint32_t idesc = (1u << 4) | (((uint32_t)(8 * g.G) >> 3) << 17) | ((128u >> 4) << 24);
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) bbels_edge_umma_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
